@@ -1,0 +1,488 @@
+// qe_engine.cu -- C ABI (include/qe_engine.h) over the kernels in qe_kernels.cuh.  Build: see build.py
+// (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "../../include/qe_engine.h"
+#include "qe_kernels.cuh"
+
+using namespace qe;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess) return fail(QE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct qe_engine {
+    int64_t S = 0;
+    int A = 0, ld = 0, lpa = 0, device = 0, sms = 0;
+    float gamma = 0.0f;
+    Table T{};
+    int cap = 0;             // per-agent scratch capacity
+    uint8_t* tr_a = nullptr;
+    float* tr_r = nullptr;
+    float* delta = nullptr;
+    // staging for *_host entry points and per-step schedules
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    uint64_t* d_thresh = nullptr;
+    float* d_lr = nullptr;
+    int sched_cap = 0;
+    uint32_t step = 0;       // global step counter (epoch / tag source)
+    int64_t launches = 0;
+    int last_grid = 0;
+    std::mutex mu;
+};
+
+static int lanes_per_agent(int A) { return A <= 4 ? 1 : (A <= 8 ? 2 : (A <= 16 ? 4 : 8)); }
+
+static int ensure_agents(qe_engine* e, int n) {
+    if (n <= e->cap) return QE_OK;
+    int cap = 1024;
+    while (cap < n) cap <<= 1;
+    CK(cudaDeviceSynchronize());
+    cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p); cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta);
+    CK(cudaMalloc(&e->T.node, sizeof(uint32_t) * cap));
+    CK(cudaMalloc(&e->T.slot, sizeof(uint64_t) * cap));
+    CK(cudaMalloc(&e->T.tr_p, sizeof(float) * cap));
+    CK(cudaMalloc(&e->tr_a, cap));
+    CK(cudaMalloc(&e->tr_r, sizeof(float) * cap));
+    CK(cudaMalloc(&e->delta, sizeof(float) * cap));
+    CK(cudaMemset(e->T.slot, 0, sizeof(uint64_t) * cap));
+    e->cap = cap;
+    return QE_OK;
+}
+static int ensure_stage(qe_engine* e, size_t bytes) {
+    if (bytes <= e->stage_bytes) return QE_OK;
+    CK(cudaDeviceSynchronize());
+    cudaFree(e->stage);
+    e->stage = nullptr;
+    e->stage_bytes = 0;
+    CK(cudaMalloc(&e->stage, bytes));
+    e->stage_bytes = bytes;
+    return QE_OK;
+}
+static int check_device_errors(qe_engine* e, cudaStream_t st) {
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, e->T.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h) {
+        CK(cudaMemsetAsync(e->T.err, 0, sizeof(int), st));
+        if (h & kErrInvalidMove) return fail(QE_ERR_INVALID_MOVE, "Invalid move.");
+        if (h & kErrEmpty) return fail(QE_ERR_EMPTY, "empty candidate or bootstrap action set");
+        return fail(QE_ERR_TIMEOUT, "TD-update dependency resolution timed out");
+    }
+    return QE_OK;
+}
+template <typename K>
+static int coop_blocks(qe_engine* e, K kernel, long long work_threads, int* out) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
+    if (per_sm < 1) return fail(QE_ERR_CUDA, "kernel cannot be made resident");
+    long long want = (work_threads + 255) / 256;
+    long long maxb = (long long)per_sm * e->sms;
+    *out = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
+    return QE_OK;
+}
+
+extern "C" {
+
+const char* qe_last_error(void) { return g_err; }
+const char* qe_build_info(void) { return "libqe_b200 sm_100a (" __DATE__ " " __TIME__ ")"; }
+uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k) { return stream_u32(seed, t, i, k); }
+
+int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, int32_t device, qe_engine_t** out) {
+    if (!out || num_states <= 0 || num_actions <= 0) return fail(QE_ERR_ARG, "state_size and action_size must be positive");
+    if (num_states >= (1ll << 31)) return fail(QE_ERR_ARG, "state_size must be < 2^31");
+    CK(cudaSetDevice(device));
+    qe_engine* e = new (std::nothrow) qe_engine();
+    if (!e) return fail(QE_ERR_ARG, "out of host memory");
+    e->S = num_states;
+    e->A = num_actions;
+    e->gamma = discount_factor;
+    e->device = device;
+    e->lpa = lanes_per_agent(num_actions);
+    e->ld = num_actions <= 32 ? 4 * e->lpa : ((num_actions + 3) / 4) * 4;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    e->sms = prop.multiProcessorCount;
+    e->T.ld = e->ld;
+    e->T.A = e->A;
+    CK(cudaMalloc(&e->T.q, sizeof(float) * (size_t)e->S * e->ld));
+    CK(cudaMemset(e->T.q, 0, sizeof(float) * (size_t)e->S * e->ld));
+    CK(cudaMalloc(&e->T.head, sizeof(uint32_t) * (size_t)e->S));
+    CK(cudaMemset(e->T.head, 0, sizeof(uint32_t) * (size_t)e->S));
+    CK(cudaMalloc(&e->T.err, sizeof(int)));
+    CK(cudaMemset(e->T.err, 0, sizeof(int)));
+    int rc = ensure_agents(e, 1024);
+    if (rc) { qe_destroy(e); return rc; }
+    *out = e;
+    return QE_OK;
+}
+
+int qe_destroy(qe_engine_t* e) {
+    if (!e) return QE_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    cudaFree(e->T.q); cudaFree(e->T.head); cudaFree(e->T.err); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
+    cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
+    delete e;
+    return QE_OK;
+}
+
+int qe_set_discount(qe_engine_t* e, float g) { e->gamma = g; return QE_OK; }
+float* qe_table_ptr(qe_engine_t* e) { return e->T.q; }
+int32_t qe_table_stride(qe_engine_t* e) { return e->ld; }
+int64_t qe_kernel_launches(qe_engine_t* e) { return e->launches; }
+int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
+
+int qe_table_upload_host(qe_engine_t* e, const float* dense) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpy2D(e->T.q, sizeof(float) * e->ld, dense, sizeof(float) * e->A, sizeof(float) * e->A, (size_t)e->S, cudaMemcpyHostToDevice));
+    return QE_OK;
+}
+int qe_table_download_host(qe_engine_t* e, float* dense) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpy2D(dense, sizeof(float) * e->A, e->T.q, sizeof(float) * e->ld, sizeof(float) * e->A, (size_t)e->S, cudaMemcpyDeviceToHost));
+    return QE_OK;
+}
+int qe_table_fill(qe_engine_t* e, float value, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    table_fill_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(e->T, e->S, value, 0u, 0);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_table_fill_random(qe_engine_t* e, uint32_t seed, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    table_fill_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(e->T, e->S, 0.0f, seed, 1);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_sync(qe_engine_t* e, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    return check_device_errors(e, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------- select
+static int select_impl(qe_engine* e, const int32_t* states, const uint32_t* mask_bits, const uint8_t* mask_bytes,
+                       const uint32_t* uniforms, int slots, uint32_t seed, uint32_t t, uint32_t agent0, uint64_t thresh,
+                       int det, int empty_all, int32_t* out, int n, cudaStream_t st) {
+    if (n <= 0) return QE_OK;
+    if (uniforms && slots < 2) return fail(QE_ERR_ARG, "uniforms need at least 2 slots");
+    Uniforms U{uniforms, slots, seed, t, agent0, seed, t};
+    if (e->A > 32 || mask_bytes) {
+        select_generic_kernel<<<(n + 127) / 128, 128, 0, st>>>(e->T, states, mask_bytes, U, thresh, det, empty_all, out, n);
+    } else {
+        const long long threads = (long long)n * e->lpa;
+        const int blocks = (int)((threads + 255) / 256 < e->sms * 16 ? (threads + 255) / 256 : e->sms * 16);
+        switch (e->lpa) {
+            case 1: select_kernel<1><<<blocks, 256, 0, st>>>(e->T, states, mask_bits, U, thresh, det, empty_all, out, n); break;
+            case 2: select_kernel<2><<<blocks, 256, 0, st>>>(e->T, states, mask_bits, U, thresh, det, empty_all, out, n); break;
+            case 4: select_kernel<4><<<blocks, 256, 0, st>>>(e->T, states, mask_bits, U, thresh, det, empty_all, out, n); break;
+            default: select_kernel<8><<<blocks, 256, 0, st>>>(e->T, states, mask_bits, U, thresh, det, empty_all, out, n); break;
+        }
+    }
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+
+int qe_select(qe_engine_t* e, const int32_t* states, const uint32_t* mask_bits, const uint8_t* mask_bytes,
+              const uint32_t* uniforms, int32_t slots, uint32_t stream_seed, uint32_t t, uint32_t agent0,
+              uint64_t explore_threshold, int32_t deterministic, int32_t empty_all, int32_t* actions_out, int32_t n,
+              void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->device));
+    return select_impl(e, states, mask_bits, mask_bytes, uniforms, slots, stream_seed, t, agent0, explore_threshold,
+                       deterministic, empty_all, actions_out, n, (cudaStream_t)stream);
+}
+
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int qe_select_host(qe_engine_t* e, const int32_t* states, const uint32_t* mask_bits, const uint8_t* mask_bytes,
+                   const uint32_t* uniforms, int32_t slots, uint32_t stream_seed, uint32_t t, uint32_t agent0,
+                   uint64_t explore_threshold, int32_t deterministic, int32_t empty_all, int32_t* actions_out, int32_t n) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n <= 0) return QE_OK;
+    CK(cudaSetDevice(e->device));
+    const size_t b_s = al(sizeof(int32_t) * n), b_m = mask_bits ? al(sizeof(uint32_t) * n) : 0,
+                 b_mb = mask_bytes ? al((size_t)n * e->A) : 0, b_u = uniforms ? al(sizeof(uint32_t) * (size_t)n * slots) : 0,
+                 b_o = al(sizeof(int32_t) * n);
+    int rc = ensure_stage(e, b_s + b_m + b_mb + b_u + b_o);
+    if (rc) return rc;
+    char* p = (char*)e->stage;
+    int32_t* d_s = (int32_t*)p; p += b_s;
+    uint32_t* d_m = mask_bits ? (uint32_t*)p : nullptr; p += b_m;
+    uint8_t* d_mb = mask_bytes ? (uint8_t*)p : nullptr; p += b_mb;
+    uint32_t* d_u = uniforms ? (uint32_t*)p : nullptr; p += b_u;
+    int32_t* d_o = (int32_t*)p;
+    cudaStream_t st = 0;
+    CK(cudaMemcpyAsync(d_s, states, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    if (d_m) CK(cudaMemcpyAsync(d_m, mask_bits, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    if (d_mb) CK(cudaMemcpyAsync(d_mb, mask_bytes, (size_t)n * e->A, cudaMemcpyHostToDevice, st));
+    if (d_u) CK(cudaMemcpyAsync(d_u, uniforms, sizeof(uint32_t) * (size_t)n * slots, cudaMemcpyHostToDevice, st));
+    rc = select_impl(e, d_s, d_m, d_mb, d_u, slots, stream_seed, t, agent0, explore_threshold, deterministic, empty_all, d_o, n, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(actions_out, d_o, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return QE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- learn
+}  // extern "C"
+template <int LPA>
+static int launch_learn_exact(qe_engine* e, const int32_t* s, const int32_t* a, const float* r, const int32_t* s2,
+                              const uint8_t* term, const uint32_t* m2, float lr, int n, cudaStream_t st) {
+    int blocks = 0;
+    int rc = coop_blocks(e, learn_exact_kernel<LPA>, (long long)n * LPA, &blocks);
+    if (rc) return rc;
+    const uint32_t gstep = e->step++;
+    uint32_t tag = gstep % 255u + 1u, epoch = gstep + 1u;
+    int wipe = (tag == 1u && gstep != 0u) ? 1 : 0;
+    Table T = e->T;
+    int64_t S = e->S;
+    float gamma = e->gamma;
+    void* args[] = {&T, &S, &s, &a, &r, &s2, &term, &m2, &lr, &gamma, &tag, &epoch, &wipe, &n};
+    CK(cudaLaunchCooperativeKernel((void*)learn_exact_kernel<LPA>, dim3(blocks), dim3(256), args, 0, st));
+    e->launches++;
+    return QE_OK;
+}
+
+extern "C" {
+static int learn_impl(qe_engine* e, const int32_t* s, const int32_t* a, const float* r, const int32_t* s2, const uint8_t* term,
+                      const uint32_t* m2, const uint8_t* m2b, float lr, int n, int mode, cudaStream_t st) {
+    if (n <= 0) return QE_OK;
+    if (n >= (1 << 24)) return fail(QE_ERR_ARG, "at most 2^24-1 agents per call");
+    int rc = ensure_agents(e, n);
+    if (rc) return rc;
+    if (mode == QE_LEARN_ACCUMULATE) {
+        learn_delta_kernel<<<(n + 255) / 256, 256, 0, st>>>(e->T, s, a, r, s2, term, m2b, m2, lr, e->gamma, e->delta, n);
+        learn_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(e->T, s, a, e->delta, n);
+        e->launches += 2;
+        CK(cudaGetLastError());
+        return QE_OK;
+    }
+    if (mode != QE_LEARN_SEQUENTIAL) return fail(QE_ERR_ARG, "unknown learn mode %d", mode);
+    if (e->A > 32 || m2b) {
+        learn_sequential_kernel<<<1, 32, 0, st>>>(e->T, s, a, r, s2, term, m2b, m2, lr, e->gamma, n);
+        e->launches++;
+        CK(cudaGetLastError());
+        return QE_OK;
+    }
+    switch (e->lpa) {
+        case 1: return launch_learn_exact<1>(e, s, a, r, s2, term, m2, lr, n, st);
+        case 2: return launch_learn_exact<2>(e, s, a, r, s2, term, m2, lr, n, st);
+        case 4: return launch_learn_exact<4>(e, s, a, r, s2, term, m2, lr, n, st);
+        default: return launch_learn_exact<8>(e, s, a, r, s2, term, m2, lr, n, st);
+    }
+}
+
+int qe_learn(qe_engine_t* e, const int32_t* states, const int32_t* actions, const float* rewards, const int32_t* next_states,
+             const uint8_t* terminated, const uint32_t* next_mask_bits, const uint8_t* next_mask_bytes, float lr, int32_t n,
+             int32_t mode, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->device));
+    return learn_impl(e, states, actions, rewards, next_states, terminated, next_mask_bits, next_mask_bytes, lr, n, mode,
+                      (cudaStream_t)stream);
+}
+
+int qe_learn_host(qe_engine_t* e, const int32_t* states, const int32_t* actions, const float* rewards,
+                  const int32_t* next_states, const uint8_t* terminated, const uint32_t* next_mask_bits,
+                  const uint8_t* next_mask_bytes, float lr, int32_t n, int32_t mode) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n <= 0) return QE_OK;
+    CK(cudaSetDevice(e->device));
+    const size_t b4 = al(sizeof(int32_t) * n), b1 = al(n), b_m = next_mask_bits ? b4 : 0,
+                 b_mb = next_mask_bytes ? al((size_t)n * e->A) : 0;
+    int rc = ensure_stage(e, 4 * b4 + b1 + b_m + b_mb);
+    if (rc) return rc;
+    char* p = (char*)e->stage;
+    int32_t* d_s = (int32_t*)p; p += b4;
+    int32_t* d_a = (int32_t*)p; p += b4;
+    float* d_r = (float*)p; p += b4;
+    int32_t* d_s2 = (int32_t*)p; p += b4;
+    uint8_t* d_t = (uint8_t*)p; p += b1;
+    uint32_t* d_m = next_mask_bits ? (uint32_t*)p : nullptr; p += b_m;
+    uint8_t* d_mb = next_mask_bytes ? (uint8_t*)p : nullptr;
+    cudaStream_t st = 0;
+    CK(cudaMemcpyAsync(d_s, states, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_a, actions, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_r, rewards, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_s2, next_states, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_t, terminated, n, cudaMemcpyHostToDevice, st));
+    if (d_m) CK(cudaMemcpyAsync(d_m, next_mask_bits, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    if (d_mb) CK(cudaMemcpyAsync(d_mb, next_mask_bytes, (size_t)n * e->A, cudaMemcpyHostToDevice, st));
+    rc = learn_impl(e, d_s, d_a, d_r, d_s2, d_t, d_m, d_mb, lr, n, mode, st);
+    if (rc) return rc;
+    return check_device_errors(e, st);
+}
+
+int qe_gather(qe_engine_t* e, const int32_t* states, const int32_t* actions, float* out, int32_t n, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n <= 0) return QE_OK;
+    gather_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->T, states, actions, out, n);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+
+int qe_gather_rows_host(qe_engine_t* e, const int32_t* states_host, float* out_host, int32_t n) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n <= 0) return QE_OK;
+    CK(cudaSetDevice(e->device));
+    const size_t b_s = al(sizeof(int32_t) * n), b_o = al(sizeof(float) * (size_t)n * e->A);
+    int rc = ensure_stage(e, b_s + b_o);
+    if (rc) return rc;
+    int32_t* d_s = (int32_t*)e->stage;
+    float* d_o = (float*)((char*)e->stage + b_s);
+    CK(cudaMemcpyAsync(d_s, states_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, 0));
+    gather_rows_kernel<<<e->sms * 4, 256>>>(e->T, d_s, d_o, n);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_host, d_o, sizeof(float) * (size_t)n * e->A, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return QE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- environments
+int qe_ttt_reset(uint32_t* boards, int32_t* states_out, uint32_t* mask_bits_out, const uint32_t* uniforms, int32_t slots,
+                 uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t n, void* stream) {
+    if (n <= 0) return QE_OK;
+    if (uniforms && slots < 5) return fail(QE_ERR_ARG, "TicTacToe needs 5 uniform slots");
+    Uniforms U{uniforms, slots, stream_seed, t, agent0, stream_seed, t};
+    ttt_reset_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boards, states_out, mask_bits_out, U, n);
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_ttt_step(qe_engine_t* e, uint32_t* boards, const int32_t* actions, const uint32_t* uniforms, int32_t slots,
+                uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t* next_states, uint32_t* next_mask_bits,
+                float* rewards, uint8_t* terminated, int32_t n, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n <= 0) return QE_OK;
+    if (uniforms && slots < 5) return fail(QE_ERR_ARG, "TicTacToe needs 5 uniform slots");
+    Uniforms U{uniforms, slots, stream_seed, t, agent0, stream_seed, t};
+    ttt_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boards, actions, U, next_states, next_mask_bits, rewards,
+                                                                    terminated, e->T.err, n);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_mdp_reset(int32_t* states, uint32_t* mask_bits_out, int64_t num_states, int32_t num_actions, uint32_t env_seed,
+                 const uint32_t* uniforms, int32_t slots, uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t n,
+                 void* stream) {
+    if (n <= 0) return QE_OK;
+    if (uniforms && slots < 4) return fail(QE_ERR_ARG, "the hash MDP needs 4 uniform slots");
+    Uniforms U{uniforms, slots, stream_seed, t, agent0, stream_seed, t};
+    mdp_reset_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(states, mask_bits_out, (uint32_t)num_states, num_actions,
+                                                                     env_seed, U, n);
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t num_states, int32_t num_actions,
+                uint32_t env_seed, uint64_t term_threshold, const uint32_t* uniforms, int32_t slots, uint32_t stream_seed,
+                uint32_t t, uint32_t agent0, uint32_t* next_mask_bits, float* rewards, uint8_t* terminated, int32_t n,
+                void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n <= 0) return QE_OK;
+    if (uniforms && slots < 4) return fail(QE_ERR_ARG, "the hash MDP needs 4 uniform slots");
+    Uniforms U{uniforms, slots, stream_seed, t, agent0, stream_seed, t};
+    mdp_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(states, actions, (uint32_t)num_states, num_actions, env_seed,
+                                                                    term_threshold, U, next_mask_bits, rewards, terminated,
+                                                                    e->T.err, n);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- fused loop
+}  // extern "C"
+template <int ENV, int LPA>
+static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
+    int blocks = 0;
+    int rc = coop_blocks(e, fused_kernel<ENV, LPA>, (long long)F.n * LPA, &blocks);
+    if (rc) return rc;
+    Table T = e->T;
+    void* args[] = {&T, &F};
+    CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPA>, dim3(blocks), dim3(256), args, 0, st));
+    e->launches++;
+    e->last_grid = blocks;
+    return QE_OK;
+}
+template <int ENV>
+static int launch_fused_env(qe_engine* e, FusedArgs& F, cudaStream_t st) {
+    switch (e->lpa) {
+        case 1: return launch_fused<ENV, 1>(e, F, st);
+        case 2: return launch_fused<ENV, 2>(e, F, st);
+        case 4: return launch_fused<ENV, 4>(e, F, st);
+        default: return launch_fused<ENV, 8>(e, F, st);
+    }
+}
+
+extern "C" {
+int qe_fused_steps(qe_engine_t* e, const qe_agents_t* ag, const qe_run_t* run, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!ag || !run) return fail(QE_ERR_ARG, "null argument");
+    if (run->steps <= 0) return QE_OK;
+    if (e->A > 32) return fail(QE_ERR_ARG, "the fused loop supports at most 32 actions");
+    const int n = ag->num_agents;
+    if (n <= 0 || n >= (1 << 24)) return fail(QE_ERR_ARG, "num_agents must be in [1, 2^24)");
+    if (ag->env_kind == QE_ENV_TTT && (e->A != 9 || e->S != 19683)) return fail(QE_ERR_ARG, "TicTacToe needs a 19683 x 9 table");
+    if (ag->env_kind == QE_ENV_MDP && (uint64_t)e->S * (uint64_t)e->A >= (1ull << 32)) return fail(QE_ERR_ARG, "hash MDP needs S*A < 2^32");
+    if (ag->env_kind != QE_ENV_MDP && !ag->env_words) return fail(QE_ERR_ARG, "env_words required");
+    const int need_slots = ag->env_kind == QE_ENV_TTT ? 5 : (ag->env_kind == QE_ENV_MDP ? 4 : 2);
+    if (run->uniforms && run->slots < need_slots) return fail(QE_ERR_ARG, "uniforms need %d slots", need_slots);
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_agents(e, n);
+    if (rc) return rc;
+    if (run->steps > e->sched_cap) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(e->d_thresh); cudaFree(e->d_lr);
+        int cap = 256;
+        while (cap < run->steps) cap <<= 1;
+        CK(cudaMalloc(&e->d_thresh, sizeof(uint64_t) * cap));
+        CK(cudaMalloc(&e->d_lr, sizeof(float) * cap));
+        e->sched_cap = cap;
+    }
+    CK(cudaMemcpyAsync(e->d_thresh, run->explore_thresholds_host, sizeof(uint64_t) * run->steps, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_lr, run->learning_rates_host, sizeof(float) * run->steps, cudaMemcpyHostToDevice, st));
+    FusedArgs F{};
+    F.env_kind = ag->env_kind; F.n = n; F.steps = run->steps;
+    F.st_a = ag->states; F.st_b = ag->states_scratch; F.envw = ag->env_words; F.ep_ret = ag->episode_returns;
+    F.tr_a = e->tr_a; F.tr_r = e->tr_r;
+    F.env_seed = ag->env_seed; F.episode_len = ag->episode_len; F.term_thresh = ag->term_threshold; F.S = e->S;
+    F.eps_thresh = e->d_thresh; F.lr = e->d_lr;
+    F.uniforms = run->uniforms; F.slots = run->slots; F.stream_seed = run->stream_seed; F.t0 = run->t0; F.agent0 = run->agent0;
+    F.env_stream_seed = run->env_stream_seed; F.env_t0 = run->env_t0;
+    F.empty_all = run->empty_all; F.use_masks = run->use_masks; F.gamma = e->gamma;
+    F.step0 = e->step;
+    F.trace_actions = run->trace_actions; F.trace_rewards = run->trace_rewards; F.trace_term = run->trace_terminated;
+    F.trace_next = run->trace_next_states; F.trace_epret = run->trace_episode_returns;
+    F.ep_sum = run->episode_sum; F.ep_count = run->episode_count;
+    if ((F.ep_sum == nullptr) != (F.ep_count == nullptr)) return fail(QE_ERR_ARG, "episode_sum and episode_count go together");
+    e->step += (uint32_t)run->steps;
+    switch (ag->env_kind) {
+        case QE_ENV_MDP: return launch_fused_env<0>(e, F, st);
+        case QE_ENV_TTT: return launch_fused_env<1>(e, F, st);
+        case QE_ENV_BANDIT: return launch_fused_env<2>(e, F, st);
+        default: return fail(QE_ERR_ARG, "unknown env kind %d", ag->env_kind);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/*
+ * qe_engine.h -- C ABI of the B200-native tabular Q-learning engine (libqe_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of j-moralejo-pinas/dist_classicrl: masked epsilon-greedy
+ * select -> vector env step -> sequential TD update.  Each entry point names the reference
+ * interface it replaces (paths relative to /root/reference/src/dist_classicrl):
+ *
+ *   QLO = algorithms/base_algorithms/q_learning_optimal.py      BRT = algorithms/runtime/base_runtime.py
+ *   STR = algorithms/runtime/single_thread_runtime.py           TTT = environments/tiktaktoe_mod.py
+ *   FLT = wrappers/flatten_multidiscrete_wrapper.py             UTL = utils.py
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Pointers are DEVICE pointers unless the
+ * function name ends in `_host`.  `stream` is a cudaStream_t passed as void* (NULL = default stream); calls
+ * are asynchronous on it unless stated.  Every function returns 0 on success or a negative QE_ERR_* code;
+ * qe_last_error() returns a thread-local message.  The engine is not re-entrant per handle: calls on one
+ * handle are serialised by an internal mutex (the reference's MPI trainer calls choose_actions and learn
+ * from two host threads, q_learning_async_dist.py:434-440).
+ *
+ * Random numbers: every stochastic decision consumes one uint32 U[t][i][k] (vector step t, agent i, slot k;
+ * slot 0 explore test, 1 pick, 2.. environment; see oracle/rng.py).  `uniforms` is either a pre-drawn device
+ * array for this call or NULL, in which case U is the counter hash qe_stream_u32(seed, t, agent0 + i, k).
+ */
+#ifndef QE_ENGINE_H
+#define QE_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QE_OK 0
+#define QE_ERR_ARG (-1)          /* bad argument (reference: AssertionError / ValueError) */
+#define QE_ERR_CUDA (-2)         /* CUDA runtime error, see qe_last_error() */
+#define QE_ERR_INVALID_MOVE (-3) /* env got an illegal action (reference: AssertionError "Invalid move.", TTT:130) */
+#define QE_ERR_EMPTY (-4)        /* empty candidate / bootstrap set (reference: IndexError / np.max of empty, QLO:470,764) */
+#define QE_ERR_TIMEOUT (-5)      /* dependency resolution did not converge (internal) */
+
+#define QE_ENV_MDP 0    /* synthetic integer-hash MDP */
+#define QE_ENV_TTT 1    /* TicTacToeEnv + FlattenMultiDiscreteObservationsWrapper + SyncVectorEnv(SAME_STEP) */
+#define QE_ENV_BANDIT 2 /* RiggedTwoArmedBanditEnv in DummyVecWrapper (rigged_two_armed_bandit.py:55-80) */
+
+#define QE_LEARN_SEQUENTIAL 0 /* learn / learn_iter: exact per-agent order (QLO:770-817, 893-934) */
+#define QE_LEARN_ACCUMULATE 1 /* learn_vec / _learn_vec: snapshot bootstrap + np.add.at (QLO:853-891) */
+
+typedef struct qe_engine qe_engine_t;
+
+/* ---- lifetime / table: replaces OptimalQLearningBase.__init__ and the q_table attribute (QLO:84-98, :80) ---- */
+int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, int32_t device, qe_engine_t** out);
+int qe_destroy(qe_engine_t* e);
+const char* qe_last_error(void);
+int qe_set_discount(qe_engine_t* e, float discount_factor);
+/* fp32 table in HBM, row-major with a padded row stride (in floats); rows are 16-byte aligned */
+float* qe_table_ptr(qe_engine_t* e);
+int32_t qe_table_stride(qe_engine_t* e);
+int qe_table_upload_host(qe_engine_t* e, const float* dense_host /* [S][A] */);   /* q_table setter; synchronous */
+int qe_table_download_host(qe_engine_t* e, float* dense_host /* [S][A] */);       /* q_table getter / save(); synchronous */
+int qe_table_fill(qe_engine_t* e, float value, void* stream);
+/* throughput runs: table[s][a] = (stream hash >> 8) * 2^-24, uniform in [0,1) */
+int qe_table_fill_random(qe_engine_t* e, uint32_t seed, void* stream);
+int qe_sync(qe_engine_t* e, void* stream); /* cudaStreamSynchronize + raise deferred device errors */
+
+/* ---- select: replaces choose_actions and its 8 variants (QLO:263-726) ------------------------------------
+ * mask_bits[N]: bit a set = action a legal (A <= 32), NULL = no masks.  mask_bytes[N][A] (uint8 truthy) is the
+ * general form, required when A > 32.  explore_threshold = ceil(eps * 2^32) clamped to [0, 2^32].
+ * empty_all: 0 -> all-zero mask yields -1 (QLO:348); 1 -> every action ties (QLO:467-470).  actions_out int32[N]. */
+int qe_select(qe_engine_t* e, const int32_t* states, const uint32_t* mask_bits, const uint8_t* mask_bytes,
+              const uint32_t* uniforms, int32_t slots, uint32_t stream_seed, uint32_t t, uint32_t agent0,
+              uint64_t explore_threshold, int32_t deterministic, int32_t empty_all, int32_t* actions_out, int32_t n,
+              void* stream);
+/* same with HOST buffers (what BaseRuntime._choose_actions hands over, BRT:265-291); synchronous */
+int qe_select_host(qe_engine_t* e, const int32_t* states, const uint32_t* mask_bits, const uint8_t* mask_bytes,
+                   const uint32_t* uniforms, int32_t slots, uint32_t stream_seed, uint32_t t, uint32_t agent0,
+                   uint64_t explore_threshold, int32_t deterministic, int32_t empty_all, int32_t* actions_out, int32_t n);
+
+/* ---- learn: replaces learn / learn_iter / single_learn and learn_vec (QLO:728-934) -------------------------
+ * terminated: uint8[N]; next_mask_bits / next_mask_bytes as in qe_select (NULL, NULL = unmasked max). */
+int qe_learn(qe_engine_t* e, const int32_t* states, const int32_t* actions, const float* rewards,
+             const int32_t* next_states, const uint8_t* terminated, const uint32_t* next_mask_bits,
+             const uint8_t* next_mask_bytes, float lr, int32_t n, int32_t mode, void* stream);
+int qe_learn_host(qe_engine_t* e, const int32_t* states, const int32_t* actions, const float* rewards,
+                  const int32_t* next_states, const uint8_t* terminated, const uint32_t* next_mask_bits,
+                  const uint8_t* next_mask_bytes, float lr, int32_t n, int32_t mode);
+
+/* ---- accessors: get_q_values / add_q_values ... (QLO:100-250); device index arrays ---- */
+int qe_gather(qe_engine_t* e, const int32_t* states, const int32_t* actions, float* out, int32_t n, void* stream);
+/* get_states_q_values (QLO:154-171) with HOST buffers: out_host[n][A]; synchronous */
+int qe_gather_rows_host(qe_engine_t* e, const int32_t* states_host, float* out_host, int32_t n);
+
+/* ---- environments (device-resident state): replace env.reset / env.step of the bundled envs ---------------- */
+/* TicTacToe boards: 2 bits per cell (cell c at bits 2c..2c+1), bit 18 = agent_mark - 1.  uniforms as above
+ * (slots 2: machine move, 3: who starts, 4: machine opening). */
+int qe_ttt_reset(uint32_t* boards, int32_t* states_out, uint32_t* mask_bits_out, const uint32_t* uniforms, int32_t slots,
+                 uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t n, void* stream);
+int qe_ttt_step(qe_engine_t* e, uint32_t* boards, const int32_t* actions, const uint32_t* uniforms, int32_t slots,
+                uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t* next_states, uint32_t* next_mask_bits,
+                float* rewards, uint8_t* terminated, int32_t n, void* stream);
+/* hash MDP: slots 2: termination draw, 3: (re)start state */
+int qe_mdp_reset(int32_t* states, uint32_t* mask_bits_out, int64_t num_states, int32_t num_actions, uint32_t env_seed,
+                 const uint32_t* uniforms, int32_t slots, uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t n,
+                 void* stream);
+int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t num_states, int32_t num_actions,
+                uint32_t env_seed, uint64_t term_threshold, const uint32_t* uniforms, int32_t slots, uint32_t stream_seed,
+                uint32_t t, uint32_t agent0, uint32_t* next_mask_bits, float* rewards, uint8_t* terminated, int32_t n,
+                void* stream);
+
+/* ---- fused loop: replaces the body of SingleThreadQLearning.run_steps (STR:63-64) =
+ *      BaseRuntime.run_single_step (BRT:184-222) x steps, one persistent cooperative kernel ------------------- */
+typedef struct {
+    int32_t env_kind;          /* QE_ENV_* */
+    int32_t num_agents;        /* N <= 2^24 - 1 */
+    int32_t* states;           /* [N] current observation; updated in place */
+    int32_t* states_scratch;   /* [N] */
+    uint32_t* env_words;       /* [N] TicTacToe board / bandit step counter; NULL for the MDP */
+    float* episode_returns;    /* [N] agent_rewards accumulator (STR:57, BRT:212); updated in place */
+    uint32_t env_seed;         /* MDP */
+    uint32_t episode_len;      /* bandit */
+    uint64_t term_threshold;   /* MDP: ceil(p_term * 2^32) */
+} qe_agents_t;
+
+typedef struct {
+    int32_t steps;                    /* K vector steps in this launch */
+    const uint64_t* explore_thresholds_host; /* [K] ceil(eps_t * 2^32)   (schedules evaluated by the caller, BRT:262-263) */
+    const float* learning_rates_host;        /* [K] float32(lr_t) */
+    const uint32_t* uniforms;         /* device [K][N][slots] or NULL -> counter stream */
+    int32_t slots;
+    uint32_t stream_seed, t0, agent0; /* select stream (slots 0,1): U[t0 + k][agent0 + i] */
+    uint32_t env_stream_seed, env_t0; /* environment stream (slots >= 2) */
+    int32_t empty_all;
+    int32_t use_masks;                /* 0: every action legal (plain-array observations, BRT:255-259) */
+    /* optional per-step traces, device [K][N]; NULL = not recorded */
+    int32_t* trace_actions;
+    float* trace_rewards;
+    uint8_t* trace_terminated;
+    int32_t* trace_next_states;
+    float* trace_episode_returns;     /* NaN where no episode finished, else the finished episode's return (BRT:218-221) */
+    /* optional statistics (device scalars, accumulated): sum / count of finished-episode returns */
+    double* episode_sum;
+    unsigned long long* episode_count;
+} qe_run_t;
+
+int qe_fused_steps(qe_engine_t* e, const qe_agents_t* agents, const qe_run_t* run, void* stream);
+
+/* introspection for benchmarks / tests */
+uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k);
+int64_t qe_kernel_launches(qe_engine_t* e);     /* kernels launched by this handle so far */
+int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch */
+const char* qe_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QE_ENGINE_H */
