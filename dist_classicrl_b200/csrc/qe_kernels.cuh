@@ -114,7 +114,6 @@ __device__ __forceinline__ void learn_resolve(const Table& T, int i, int s, int 
         if (pj >= 0) { w = ld_relaxed_u64(T.slot + pj); if ((w >> 32) != want) ok = false; else pe = __uint_as_float((uint32_t)w); }
         if (group_all<LPA>(ok, gm)) { m = ml; break; }
         if (++spins > kSpinLimit) { if (l == 0) atomicOr(T.err, kErrTimeout); m = ml; break; }
-        __nanosleep(40);
     }
     m = group_max<LPA>(m, gm);
     const float v = td_value(pe, r, term ? 0.0f : m, lr, gamma);
@@ -200,10 +199,15 @@ __global__ void __launch_bounds__(256) learn_exact_kernel(Table T, int64_t S, co
     const uint32_t gm = group_mask<LPA>();
     const int groups = nthreads / LPA;
     const uint32_t full = T.A >= 32 ? 0xFFFFFFFFu : ((1u << T.A) - 1u);
-    for (int i = tid / LPA; i < n; i += groups) {
-        const uint32_t m2 = next_mask_bits ? (next_mask_bits[i] & full) : full;
-        learn_resolve<LPA>(T, i, states[i], actions[i], rewards[i], T.tr_p[i], next_states[i], terminated[i] != 0, m2, lr,
-                           gamma, tag, epoch, gm);
+    const int gl = (threadIdx.x & 31) / LPA;
+    for (int ib = (tid / 32) * (32 / LPA); ib < n; ib += groups) {
+        const int i = ib + gl;
+        if (i < n) {
+            const uint32_t m2 = next_mask_bits ? (next_mask_bits[i] & full) : full;
+            learn_resolve<LPA>(T, i, states[i], actions[i], rewards[i], T.tr_p[i], next_states[i], terminated[i] != 0, m2, lr,
+                               gamma, tag, epoch, gm);
+        }
+        __syncwarp();
     }
 }
 
@@ -381,7 +385,8 @@ __global__ void __launch_bounds__(256) fused_kernel(Table T, FusedArgs F) {
     const int l = threadIdx.x & (LPA - 1);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int groups = (gridDim.x * blockDim.x) / LPA;
-    const int g0 = tid / LPA;
+    const int gl = (threadIdx.x & 31) / LPA;      // group within the warp
+    const int gw0 = (tid / 32) * (32 / LPA);       // first group of this warp
     const uint32_t full = T.A >= 32 ? 0xFFFFFFFFu : ((1u << T.A) - 1u);
     const int n = F.n;
 
@@ -400,7 +405,9 @@ __global__ void __launch_bounds__(256) fused_kernel(Table T, FusedArgs F) {
         unsigned int loc_cnt = 0;
 
         // ---------------- phase A: select + env step + writer-list insert
-        for (int i = g0; i < n; i += groups) {
+        for (int ib = gw0; ib < n; ib += groups) {
+            const int i = ib + gl;
+            if (i < n) {
             const int s = cur[i];
             uint32_t ew = (ENV == 0) ? 0u : F.envw[i];
             const uint32_t valid = F.use_masks ? env_mask<ENV>(s, ew, T.A, F.env_seed) : full;
@@ -443,6 +450,8 @@ __global__ void __launch_bounds__(256) fused_kernel(Table T, FusedArgs F) {
                 if (F.trace_epret) F.trace_epret[o] = fin;
                 if (ok) list_insert(T, i, s, a, p, tag);
             }
+            }
+            __syncwarp();  // reconverge the lane groups every iteration
         }
         if (F.ep_count) {  // block-level reduction of the episode statistics, one atomic per block
             for (int d = 16; d > 0; d >>= 1) {
@@ -461,13 +470,18 @@ __global__ void __launch_bounds__(256) fused_kernel(Table T, FusedArgs F) {
         grid.sync();
 
         // ---------------- phase B: exact sequential TD update (resolve + commit)
-        for (int i = g0; i < n; i += groups) {
-            const uint8_t at = F.tr_a[i];
-            if (at & 0x40) continue;  // agent had no legal action (error already flagged)
-            const int s2 = nxt[i];
-            const uint32_t ew = (ENV == 1) ? F.envw[i] : 0u;
-            const uint32_t m2 = F.use_masks ? env_mask<ENV>(s2, ew, T.A, F.env_seed) : full;
-            learn_resolve<LPA>(T, i, cur[i], at & 0x3F, F.tr_r[i], T.tr_p[i], s2, (at & 0x80) != 0, m2, lr, F.gamma, tag, epoch, gm);
+        for (int ib = gw0; ib < n; ib += groups) {
+            const int i = ib + gl;
+            if (i < n) {
+                const uint8_t at = F.tr_a[i];
+                if (!(at & 0x40)) {  // else: agent had no legal action (error already flagged)
+                    const int s2 = nxt[i];
+                    const uint32_t ew = (ENV == 1) ? F.envw[i] : 0u;
+                    const uint32_t m2 = F.use_masks ? env_mask<ENV>(s2, ew, T.A, F.env_seed) : full;
+                    learn_resolve<LPA>(T, i, cur[i], at & 0x3F, F.tr_r[i], T.tr_p[i], s2, (at & 0x80) != 0, m2, lr, F.gamma, tag, epoch, gm);
+                }
+            }
+            __syncwarp();
         }
         grid.sync();
     }

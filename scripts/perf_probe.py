@@ -1,0 +1,56 @@
+"""Quick device-only timing of the fused loop at the C-ABI level (development aid)."""
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+from dist_classicrl_b200 import capi
+
+S, A, N, K = int(float(sys.argv[1])), int(sys.argv[2]), int(float(sys.argv[3])), int(sys.argv[4])
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+lib = capi.lib()
+h = C.c_void_p()
+capi.check(lib.qe_create(S, A, 0.99, 0, C.byref(h)))
+capi.check(lib.qe_table_fill_random(h, 1, None))
+dev = torch.device("cuda:0")
+states = torch.empty(N, dtype=torch.int32, device=dev)
+scratch = torch.empty_like(states)
+ep = torch.zeros(N, dtype=torch.float32, device=dev)
+capi.check(lib.qe_mdp_reset(states.data_ptr(), None, S, A, 0, None, 4, 0, 0xFFFFFFFF, 0, N, None))
+th = np.full(K, int(np.ceil(0.1 * 2**32)), dtype=np.uint64)
+lr = np.full(K, 0.1, dtype=np.float32)
+ag = capi.QeAgents(capi.QE_ENV_MDP, N, states.data_ptr(), scratch.data_ptr(), None, ep.data_ptr(), 0, 0, int(np.ceil(0.05 * 2**32)))
+es, ec = torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)
+
+
+def launch(t0, stats=True):
+    run = capi.QeRun()
+    run.steps = K
+    run.explore_thresholds_host = th.ctypes.data_as(C.c_void_p)
+    run.learning_rates_host = lr.ctypes.data_as(C.c_void_p)
+    run.slots = 4
+    run.t0 = run.env_t0 = t0
+    run.use_masks = 1
+    run.empty_all = int(A > 10)
+    if stats:
+        run.episode_sum, run.episode_count = es.data_ptr(), ec.data_ptr()
+    capi.check(lib.qe_fused_steps(h, C.byref(ag), C.byref(run), None))
+
+
+launch(0)
+capi.check(lib.qe_sync(h, None))
+best = 1e9
+for r in range(reps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    launch((r + 1) * K)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    best = min(best, ms)
+    print(f"rep {r}: {ms:.3f} ms for {K} steps -> {ms / K * 1e3:.1f} us/step, {N * K / ms / 1e6:.3f} G agent-steps/s")
+capi.check(lib.qe_sync(h, None))
+balg = 8 * A + 12
+print(f"grid={lib.qe_fused_grid_blocks(h)} best {N * K / best / 1e6:.3f} G agent-steps/s, alg {balg} B/agent-step -> {N * K * balg / best / 1e6:.1f} GB/s "
+      f"({N * K * balg / best / 1e6 / 6549.4 * 100:.1f}% of measured HBM peak); episodes={int(ec.item())}")
