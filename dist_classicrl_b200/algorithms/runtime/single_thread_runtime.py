@@ -37,7 +37,7 @@ class SingleThreadQLearning(BaseRuntime):
             if self.history_mode == "full":
                 mean = sum(reward_history) / len(reward_history)  # ZeroDivisionError if no episode ended (STR:67)
             else:
-                mean = self.last_episode_sum / self.last_episode_count
+                mean = self.last_episode_sum / self.last_episode_count if self.last_episode_count else 0.0
         else:
             for _ in range(steps):
                 states, infos = self.run_single_step(env, states, agent_rewards, reward_history)

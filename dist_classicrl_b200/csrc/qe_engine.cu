@@ -37,6 +37,7 @@ struct qe_engine {
     // staging for *_host entry points and per-step schedules
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    int* tile_counter = nullptr;  // [2]
     uint64_t* d_thresh = nullptr;
     float* d_lr = nullptr;
     int sched_cap = 0;
@@ -114,7 +115,19 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     e->gamma = discount_factor;
     e->device = device;
     e->lpa = lanes_per_agent(num_actions);
-    e->ld = num_actions <= 32 ? 4 * e->lpa : ((num_actions + 3) / 4) * 4;
+    if (num_actions <= 32) {
+        // row block: [4*LPA floats of Q][8 words of writer info][spare inline entries], power-of-two sized
+        const int info_off = 4 * e->lpa < 8 ? 8 : 4 * e->lpa;  // 32-byte aligned
+        int ld = 16;
+        while (ld < info_off + 8) ld <<= 1;
+        e->ld = ld;
+        e->T.info_off = info_off;
+        e->T.inline_cap = 4 + (ld - info_off - 8);
+    } else {  // generic path (sequential learn kernel): plain padded rows, no writer info
+        e->ld = ((num_actions + 3) / 4) * 4;
+        e->T.info_off = 0;
+        e->T.inline_cap = 0;
+    }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     e->sms = prop.multiProcessorCount;
@@ -122,10 +135,10 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     e->T.A = e->A;
     CK(cudaMalloc(&e->T.q, sizeof(float) * (size_t)e->S * e->ld));
     CK(cudaMemset(e->T.q, 0, sizeof(float) * (size_t)e->S * e->ld));
-    CK(cudaMalloc(&e->T.head, sizeof(uint32_t) * (size_t)e->S));
-    CK(cudaMemset(e->T.head, 0, sizeof(uint32_t) * (size_t)e->S));
     CK(cudaMalloc(&e->T.err, sizeof(int)));
     CK(cudaMemset(e->T.err, 0, sizeof(int)));
+    CK(cudaMalloc(&e->tile_counter, 2 * sizeof(int)));
+    CK(cudaMemset(e->tile_counter, 0, 2 * sizeof(int)));
     int rc = ensure_agents(e, 1024);
     if (rc) { qe_destroy(e); return rc; }
     *out = e;
@@ -136,7 +149,7 @@ int qe_destroy(qe_engine_t* e) {
     if (!e) return QE_OK;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    cudaFree(e->T.q); cudaFree(e->T.head); cudaFree(e->T.err); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
+    cudaFree(e->T.q); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
     delete e;
     return QE_OK;
@@ -252,13 +265,10 @@ static int launch_learn_exact(qe_engine* e, const int32_t* s, const int32_t* a, 
     int blocks = 0;
     int rc = coop_blocks(e, learn_exact_kernel<LPA>, (long long)n * LPA, &blocks);
     if (rc) return rc;
-    const uint32_t gstep = e->step++;
-    uint32_t tag = gstep % 255u + 1u, epoch = gstep + 1u;
-    int wipe = (tag == 1u && gstep != 0u) ? 1 : 0;
+    uint32_t epoch = ++e->step;
     Table T = e->T;
-    int64_t S = e->S;
     float gamma = e->gamma;
-    void* args[] = {&T, &S, &s, &a, &r, &s2, &term, &m2, &lr, &gamma, &tag, &epoch, &wipe, &n};
+    void* args[] = {&T, &s, &a, &r, &s2, &term, &m2, &lr, &gamma, &epoch, &n};
     CK(cudaLaunchCooperativeKernel((void*)learn_exact_kernel<LPA>, dim3(blocks), dim3(256), args, 0, st));
     e->launches++;
     return QE_OK;
@@ -472,6 +482,8 @@ int qe_fused_steps(qe_engine_t* e, const qe_agents_t* ag, const qe_run_t* run, v
     F.env_stream_seed = run->env_stream_seed; F.env_t0 = run->env_t0;
     F.empty_all = run->empty_all; F.use_masks = run->use_masks; F.gamma = e->gamma;
     F.step0 = e->step;
+    F.tile_counter = e->tile_counter;
+    CK(cudaMemsetAsync(e->tile_counter, 0, 2 * sizeof(int), st));
     F.trace_actions = run->trace_actions; F.trace_rewards = run->trace_rewards; F.trace_term = run->trace_terminated;
     F.trace_next = run->trace_next_states; F.trace_epret = run->trace_episode_returns;
     F.ep_sum = run->episode_sum; F.ep_count = run->episode_count;
