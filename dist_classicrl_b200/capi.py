@@ -63,6 +63,7 @@ SIGNATURES = {
     "qe_stream_u32": (u32, [u32, u32, u32, u32]),
     "qe_kernel_launches": (i64, [vp]),
     "qe_fused_grid_blocks": (i32, [vp]),
+    "qe_fused_phase_ns": (i32, [vp, vp, i32]),
     "qe_build_info": (C.c_char_p, []),
 }
 
@@ -82,8 +83,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.OUT
-    if not _build.up_to_date():
+    path = os.environ.get("QE_LIBRARY") or _build.OUT  # QE_LIBRARY: development override (kernel variants)
+    if path == _build.OUT and not _build.up_to_date():
         try:
             _build.build()
         except Exception as exc:  # noqa: BLE001

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 
@@ -27,7 +28,7 @@ static int fail(int code, const char* fmt, ...) {
 
 struct qe_engine {
     int64_t S = 0;
-    int A = 0, ld = 0, lpa = 0, device = 0, sms = 0;
+    int A = 0, ld = 0, lpa = 0, lpr = 0, device = 0, sms = 0;  // lpa: 16-byte lanes per row (select_kernel); lpr: 32-byte sectors per row
     float gamma = 0.0f;
     Table T{};
     int cap = 0;             // per-agent scratch capacity
@@ -38,6 +39,8 @@ struct qe_engine {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     int* tile_counter = nullptr;  // [2]
+    uint64_t* phase_ns = nullptr; // [31+] fused-loop phase clock (see qe_fused_phase_ns)
+    int phase_steps = 0;
     uint64_t* d_thresh = nullptr;
     float* d_lr = nullptr;
     int sched_cap = 0;
@@ -48,6 +51,7 @@ struct qe_engine {
 };
 
 static int lanes_per_agent(int A) { return A <= 4 ? 1 : (A <= 8 ? 2 : (A <= 16 ? 4 : 8)); }
+static int sectors_per_row(int A) { return A <= 8 ? 1 : (A <= 16 ? 2 : 4); }
 
 static int ensure_agents(qe_engine* e, int n) {
     if (n <= e->cap) return QE_OK;
@@ -55,6 +59,10 @@ static int ensure_agents(qe_engine* e, int n) {
     while (cap < n) cap <<= 1;
     CK(cudaDeviceSynchronize());
     cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p); cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta);
+    cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask);
+    CK(cudaMalloc(&e->T.smask, sizeof(uint32_t) * (cap / 32)));
+    CK(cudaMalloc(&e->T.rec, sizeof(uint32_t) * 8 * (size_t)cap));
+    CK(cudaMalloc(&e->T.dmask, sizeof(uint32_t) * (cap / 32)));
     CK(cudaMalloc(&e->T.node, sizeof(uint32_t) * cap));
     CK(cudaMalloc(&e->T.slot, sizeof(uint64_t) * cap));
     CK(cudaMalloc(&e->T.tr_p, sizeof(float) * cap));
@@ -115,14 +123,17 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     e->gamma = discount_factor;
     e->device = device;
     e->lpa = lanes_per_agent(num_actions);
+    e->lpr = sectors_per_row(num_actions);
     if (num_actions <= 32) {
-        // row block: [4*LPA floats of Q][8 words of writer info][spare inline entries], power-of-two sized
-        const int info_off = 4 * e->lpa < 8 ? 8 : 4 * e->lpa;  // 32-byte aligned
-        int ld = 16;
-        while (ld < info_off + 8) ld <<= 1;
+        // row block: [8*LPR floats of Q][8 words of writer info][spare inline entries], power-of-two sized
+        const int info_off = 8 * e->lpr;  // the writer info starts on a 32-byte sector
+        // agents cluster on the deterministic environments (a greedy policy sends everybody at s to the same s'),
+        // so rows with dozens of writers are common: the block is four times the Q row (A=16: 256 B, 44 inline
+        // writer entries; A<=8: 128 B, 20 entries); only longer lists spill to the per-agent overflow list
+        const int ld = 4 * info_off;
         e->ld = ld;
         e->T.info_off = info_off;
-        e->T.inline_cap = 4 + (ld - info_off - 8);
+        e->T.inline_cap = ld - info_off - 4;
     } else {  // generic path (sequential learn kernel): plain padded rows, no writer info
         e->ld = ((num_actions + 3) / 4) * 4;
         e->T.info_off = 0;
@@ -137,8 +148,10 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     CK(cudaMemset(e->T.q, 0, sizeof(float) * (size_t)e->S * e->ld));
     CK(cudaMalloc(&e->T.err, sizeof(int)));
     CK(cudaMemset(e->T.err, 0, sizeof(int)));
-    CK(cudaMalloc(&e->tile_counter, 2 * sizeof(int)));
-    CK(cudaMemset(e->tile_counter, 0, 2 * sizeof(int)));
+    CK(cudaMalloc(&e->tile_counter, 4 * sizeof(int)));
+    CK(cudaMemset(e->tile_counter, 0, 4 * sizeof(int)));
+    CK(cudaMalloc(&e->phase_ns, 33 * sizeof(uint64_t)));
+    CK(cudaMemset(e->phase_ns, 0, 33 * sizeof(uint64_t)));
     int rc = ensure_agents(e, 1024);
     if (rc) { qe_destroy(e); return rc; }
     *out = e;
@@ -149,7 +162,7 @@ int qe_destroy(qe_engine_t* e) {
     if (!e) return QE_OK;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    cudaFree(e->T.q); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
+    cudaFree(e->T.q); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
     delete e;
     return QE_OK;
@@ -160,6 +173,15 @@ float* qe_table_ptr(qe_engine_t* e) { return e->T.q; }
 int32_t qe_table_stride(qe_engine_t* e) { return e->ld; }
 int64_t qe_kernel_launches(qe_engine_t* e) { return e->launches; }
 int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
+int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    uint64_t h[33];
+    if (cudaSetDevice(e->device) != cudaSuccess || cudaMemcpy(h, e->phase_ns, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(QE_ERR_CUDA, "cannot read the phase clock");
+    const int m = 1 + 3 * e->phase_steps;
+    for (int i = 0; i < m && i < cap; ++i) out_host[i] = h[i];
+    return m < cap ? m : cap;
+}
 
 int qe_table_upload_host(qe_engine_t* e, const float* dense) {
     std::lock_guard<std::mutex> lk(e->mu);
@@ -259,17 +281,19 @@ int qe_select_host(qe_engine_t* e, const int32_t* states, const uint32_t* mask_b
 
 // ---------------------------------------------------------------------------------------------- learn
 }  // extern "C"
-template <int LPA>
+template <int LPR>
 static int launch_learn_exact(qe_engine* e, const int32_t* s, const int32_t* a, const float* r, const int32_t* s2,
                               const uint8_t* term, const uint32_t* m2, float lr, int n, cudaStream_t st) {
     int blocks = 0;
-    int rc = coop_blocks(e, learn_exact_kernel<LPA>, (long long)n * LPA, &blocks);
+    int rc = coop_blocks(e, learn_exact_kernel<LPR>, (long long)n, &blocks);
     if (rc) return rc;
     uint32_t epoch = ++e->step;
     Table T = e->T;
     float gamma = e->gamma;
-    void* args[] = {&T, &s, &a, &r, &s2, &term, &m2, &lr, &gamma, &epoch, &n};
-    CK(cudaLaunchCooperativeKernel((void*)learn_exact_kernel<LPA>, dim3(blocks), dim3(256), args, 0, st));
+    int* cursor = e->tile_counter;
+    CK(cudaMemsetAsync(cursor, 0, 4 * sizeof(int), st));
+    void* args[] = {&T, &s, &a, &r, &s2, &term, &m2, &lr, &gamma, &epoch, &cursor, &n};
+    CK(cudaLaunchCooperativeKernel((void*)learn_exact_kernel<LPR>, dim3(blocks), dim3(256), args, 0, st));
     e->launches++;
     return QE_OK;
 }
@@ -295,11 +319,10 @@ static int learn_impl(qe_engine* e, const int32_t* s, const int32_t* a, const fl
         CK(cudaGetLastError());
         return QE_OK;
     }
-    switch (e->lpa) {
+    switch (e->lpr) {
         case 1: return launch_learn_exact<1>(e, s, a, r, s2, term, m2, lr, n, st);
         case 2: return launch_learn_exact<2>(e, s, a, r, s2, term, m2, lr, n, st);
-        case 4: return launch_learn_exact<4>(e, s, a, r, s2, term, m2, lr, n, st);
-        default: return launch_learn_exact<8>(e, s, a, r, s2, term, m2, lr, n, st);
+        default: return launch_learn_exact<4>(e, s, a, r, s2, term, m2, lr, n, st);
     }
 }
 
@@ -422,25 +445,24 @@ int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t
 
 // ---------------------------------------------------------------------------------------------- fused loop
 }  // extern "C"
-template <int ENV, int LPA>
+template <int ENV, int LPR>
 static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     int blocks = 0;
-    int rc = coop_blocks(e, fused_kernel<ENV, LPA>, (long long)F.n * LPA, &blocks);
+    int rc = coop_blocks(e, fused_kernel<ENV, LPR>, (long long)F.n, &blocks);
     if (rc) return rc;
     Table T = e->T;
     void* args[] = {&T, &F};
-    CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPA>, dim3(blocks), dim3(256), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
     e->launches++;
     e->last_grid = blocks;
     return QE_OK;
 }
 template <int ENV>
 static int launch_fused_env(qe_engine* e, FusedArgs& F, cudaStream_t st) {
-    switch (e->lpa) {
+    switch (e->lpr) {
         case 1: return launch_fused<ENV, 1>(e, F, st);
         case 2: return launch_fused<ENV, 2>(e, F, st);
-        case 4: return launch_fused<ENV, 4>(e, F, st);
-        default: return launch_fused<ENV, 8>(e, F, st);
+        default: return launch_fused<ENV, 4>(e, F, st);
     }
 }
 
@@ -483,10 +505,12 @@ int qe_fused_steps(qe_engine_t* e, const qe_agents_t* ag, const qe_run_t* run, v
     F.empty_all = run->empty_all; F.use_masks = run->use_masks; F.gamma = e->gamma;
     F.step0 = e->step;
     F.tile_counter = e->tile_counter;
-    CK(cudaMemsetAsync(e->tile_counter, 0, 2 * sizeof(int), st));
+    CK(cudaMemsetAsync(e->tile_counter, 0, 4 * sizeof(int), st));
     F.trace_actions = run->trace_actions; F.trace_rewards = run->trace_rewards; F.trace_term = run->trace_terminated;
     F.trace_next = run->trace_next_states; F.trace_epret = run->trace_episode_returns;
     F.ep_sum = run->episode_sum; F.ep_count = run->episode_count;
+    F.phase_ns = e->phase_ns;
+    e->phase_steps = run->steps < 10 ? run->steps : 10;
     if ((F.ep_sum == nullptr) != (F.ep_count == nullptr)) return fail(QE_ERR_ARG, "episode_sum and episode_count go together");
     e->step += (uint32_t)run->steps;
     switch (ag->env_kind) {

@@ -145,6 +145,10 @@ int qe_fused_steps(qe_engine_t* e, const qe_agents_t* agents, const qe_run_t* ru
 uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k);
 int64_t qe_kernel_launches(qe_engine_t* e);     /* kernels launched by this handle so far */
 int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch */
+/* phase clock of the last fused launch (synchronous): out_host[0] = %globaltimer (ns) at kernel start, then for each
+ * of the first 10 vector steps the time after phase A (select + env step + writer registration), after phase B1 (TD
+ * update, first pass) and after phase B2 (TD update, deferred agents).  Returns the number of values written. */
+int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap);
 const char* qe_build_info(void);
 
 #ifdef __cplusplus

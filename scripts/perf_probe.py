@@ -51,6 +51,12 @@ for r in range(reps):
     best = min(best, ms)
     print(f"rep {r}: {ms:.3f} ms for {K} steps -> {ms / K * 1e3:.1f} us/step, {N * K / ms / 1e6:.3f} G agent-steps/s")
 capi.check(lib.qe_sync(h, None))
+buf = (C.c_uint64 * 33)()
+m = lib.qe_fused_phase_ns(h, buf, 33)
+ts = [buf[i] for i in range(m)]
+if m >= 4:
+    for ph, name in enumerate(("A ", "B1", "B2")):
+        print(f"phase {name} us:", " ".join(f"{(ts[1 + ph + 3 * k] - ts[ph + 3 * k]) / 1e3:.1f}" for k in range((m - 1) // 3)))
 balg = 8 * A + 12
 print(f"grid={lib.qe_fused_grid_blocks(h)} best {N * K / best / 1e6:.3f} G agent-steps/s, alg {balg} B/agent-step -> {N * K * balg / best / 1e6:.1f} GB/s "
       f"({N * K * balg / best / 1e6 / 6549.4 * 100:.1f}% of measured HBM peak); episodes={int(ec.item())}")
