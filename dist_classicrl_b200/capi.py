@@ -58,8 +58,18 @@ SIGNATURES = {
     "qe_ttt_reset": (C.c_int, [vp, vp, vp, vp, i32, u32, u32, u32, i32, vp]),
     "qe_ttt_step": (C.c_int, [vp, vp, vp, vp, i32, u32, u32, u32, vp, vp, vp, vp, i32, vp]),
     "qe_mdp_reset": (C.c_int, [vp, vp, i64, i32, u32, vp, i32, u32, u32, u32, i32, vp]),
+    "qe_mdp_masks": (C.c_int, [vp, vp, i32, u32, i32, vp]),
     "qe_mdp_step": (C.c_int, [vp, vp, vp, i64, i32, u32, u64, vp, i32, u32, u32, u32, vp, vp, vp, i32, vp]),
     "qe_fused_steps": (C.c_int, [vp, C.POINTER(QeAgents), C.POINTER(QeRun), vp]),
+    "qe_set_state_base": (C.c_int, [vp, i64]),
+    "qe_set_agent_ids": (C.c_int, [vp, vp]),
+    "qe_set_hold": (C.c_int, [vp, i32]),
+    "qe_learn_commit": (C.c_int, [vp, vp, vp, i32, vp]),
+    "qe_serve_bootstrap": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, vp]),
+    "qe_table_export_dense": (C.c_int, [vp, vp, vp]),
+    "qe_table_import_dense": (C.c_int, [vp, vp, vp]),
+    "qe_table_delta_dense": (C.c_int, [vp, vp, vp, vp]),
+    "qe_table_merge_dense": (C.c_int, [vp, vp, vp, vp]),
     "qe_stream_u32": (u32, [u32, u32, u32, u32]),
     "qe_kernel_launches": (i64, [vp]),
     "qe_fused_grid_blocks": (i32, [vp]),

@@ -44,10 +44,11 @@ struct Uniforms {
     int slots;            // K
     uint32_t seed, t, agent0;
     uint32_t env_seed, env_t;
+    const uint32_t* ids = nullptr;  // optional global agent ids (sharded table: local agent i is global agent ids[i])
     __device__ __forceinline__ uint32_t draw(int i, int k) const {
         if (pre) return __ldg(pre + (size_t)i * slots + k);
-        return k < 2 ? stream_u32(seed, t, agent0 + (uint32_t)i, (uint32_t)k)
-                     : stream_u32(env_seed, env_t, agent0 + (uint32_t)i, (uint32_t)k);
+        const uint32_t g = ids ? __ldg(ids + i) : agent0 + (uint32_t)i;
+        return k < 2 ? stream_u32(seed, t, g, (uint32_t)k) : stream_u32(env_seed, env_t, g, (uint32_t)k);
     }
 };
 

@@ -30,7 +30,10 @@ struct qe_engine {
     int64_t S = 0;
     int A = 0, ld = 0, lpa = 0, lpr = 0, device = 0, sms = 0;  // lpa: 16-byte lanes per row (select_kernel); lpr: 32-byte sectors per row
     float gamma = 0.0f;
-    Table T{};
+    Table T{};               // T.q is biased by -state_base rows: kernels index it with GLOBAL state ids
+    float* q_real = nullptr; // the allocation (row 0 = state `state_base`)
+    int64_t state_base = 0;
+    const uint32_t* agent_ids = nullptr;  // optional global ids of the local agents (uniform stream), device
     int cap = 0;             // per-agent scratch capacity
     uint8_t* tr_a = nullptr;
     float* tr_r = nullptr;
@@ -50,6 +53,11 @@ struct qe_engine {
     std::mutex mu;
 };
 
+static Table local_table(const qe_engine* e) {  // rows indexed from 0 (whole-table kernels)
+    Table T = e->T;
+    T.q = e->q_real;
+    return T;
+}
 static int lanes_per_agent(int A) { return A <= 4 ? 1 : (A <= 8 ? 2 : (A <= 16 ? 4 : 8)); }
 static int sectors_per_row(int A) { return A <= 8 ? 1 : (A <= 16 ? 2 : 4); }
 
@@ -59,6 +67,8 @@ static int ensure_agents(qe_engine* e, int n) {
     while (cap < n) cap <<= 1;
     CK(cudaDeviceSynchronize());
     cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p); cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta);
+    cudaFree(e->T.later_buf);
+    CK(cudaMalloc(&e->T.later_buf, cap));
     cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask);
     CK(cudaMalloc(&e->T.smask, sizeof(uint32_t) * (cap / 32)));
     CK(cudaMalloc(&e->T.rec, sizeof(uint32_t) * 8 * (size_t)cap));
@@ -144,8 +154,9 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     e->sms = prop.multiProcessorCount;
     e->T.ld = e->ld;
     e->T.A = e->A;
-    CK(cudaMalloc(&e->T.q, sizeof(float) * (size_t)e->S * e->ld));
-    CK(cudaMemset(e->T.q, 0, sizeof(float) * (size_t)e->S * e->ld));
+    CK(cudaMalloc(&e->q_real, sizeof(float) * (size_t)e->S * e->ld));
+    CK(cudaMemset(e->q_real, 0, sizeof(float) * (size_t)e->S * e->ld));
+    e->T.q = e->q_real;
     CK(cudaMalloc(&e->T.err, sizeof(int)));
     CK(cudaMemset(e->T.err, 0, sizeof(int)));
     CK(cudaMalloc(&e->tile_counter, 4 * sizeof(int)));
@@ -162,14 +173,14 @@ int qe_destroy(qe_engine_t* e) {
     if (!e) return QE_OK;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    cudaFree(e->T.q); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
+    cudaFree(e->q_real); cudaFree(e->T.later_buf); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
     delete e;
     return QE_OK;
 }
 
 int qe_set_discount(qe_engine_t* e, float g) { e->gamma = g; return QE_OK; }
-float* qe_table_ptr(qe_engine_t* e) { return e->T.q; }
+float* qe_table_ptr(qe_engine_t* e) { return e->q_real; }
 int32_t qe_table_stride(qe_engine_t* e) { return e->ld; }
 int64_t qe_kernel_launches(qe_engine_t* e) { return e->launches; }
 int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
@@ -186,25 +197,25 @@ int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap) {
 int qe_table_upload_host(qe_engine_t* e, const float* dense) {
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->device));
-    CK(cudaMemcpy2D(e->T.q, sizeof(float) * e->ld, dense, sizeof(float) * e->A, sizeof(float) * e->A, (size_t)e->S, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(e->q_real, sizeof(float) * e->ld, dense, sizeof(float) * e->A, sizeof(float) * e->A, (size_t)e->S, cudaMemcpyHostToDevice));
     return QE_OK;
 }
 int qe_table_download_host(qe_engine_t* e, float* dense) {
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->device));
-    CK(cudaMemcpy2D(dense, sizeof(float) * e->A, e->T.q, sizeof(float) * e->ld, sizeof(float) * e->A, (size_t)e->S, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy2D(dense, sizeof(float) * e->A, e->q_real, sizeof(float) * e->ld, sizeof(float) * e->A, (size_t)e->S, cudaMemcpyDeviceToHost));
     return QE_OK;
 }
 int qe_table_fill(qe_engine_t* e, float value, void* stream) {
     std::lock_guard<std::mutex> lk(e->mu);
-    table_fill_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(e->T, e->S, value, 0u, 0);
+    table_fill_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(local_table(e), e->S, value, 0u, 0, (uint64_t)e->state_base);
     e->launches++;
     CK(cudaGetLastError());
     return QE_OK;
 }
 int qe_table_fill_random(qe_engine_t* e, uint32_t seed, void* stream) {
     std::lock_guard<std::mutex> lk(e->mu);
-    table_fill_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(e->T, e->S, 0.0f, seed, 1);
+    table_fill_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(local_table(e), e->S, 0.0f, seed, 1, (uint64_t)e->state_base);
     e->launches++;
     CK(cudaGetLastError());
     return QE_OK;
@@ -221,6 +232,7 @@ static int select_impl(qe_engine* e, const int32_t* states, const uint32_t* mask
     if (n <= 0) return QE_OK;
     if (uniforms && slots < 2) return fail(QE_ERR_ARG, "uniforms need at least 2 slots");
     Uniforms U{uniforms, slots, seed, t, agent0, seed, t};
+    U.ids = e->agent_ids;
     if (e->A > 32 || mask_bytes) {
         select_generic_kernel<<<(n + 127) / 128, 128, 0, st>>>(e->T, states, mask_bytes, U, thresh, det, empty_all, out, n);
     } else {
@@ -393,6 +405,73 @@ int qe_gather_rows_host(qe_engine_t* e, const int32_t* states_host, float* out_h
     return QE_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------- multi-GPU support
+int qe_set_state_base(qe_engine_t* e, int64_t first_state) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (first_state < 0) return fail(QE_ERR_ARG, "first_state must be >= 0");
+    e->state_base = first_state;
+    e->T.q = e->q_real - (size_t)first_state * (size_t)e->ld;  // never dereferenced outside [first_state, first_state + S)
+    return QE_OK;
+}
+int qe_set_agent_ids(qe_engine_t* e, const uint32_t* ids) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->agent_ids = ids;
+    return QE_OK;
+}
+int qe_set_hold(qe_engine_t* e, int32_t hold) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->T.hold = hold != 0;
+    return QE_OK;
+}
+int qe_learn_commit(qe_engine_t* e, const int32_t* states, const int32_t* actions, int32_t n, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n <= 0) return QE_OK;
+    if (n > e->cap) return fail(QE_ERR_ARG, "qe_learn_commit: no held update of that size");
+    learn_commit_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->T, states, actions, n);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_serve_bootstrap(qe_engine_t* e, const int32_t* rows, const int32_t* before, const uint32_t* mask_bits, float* out,
+                       int32_t n, int32_t use_versions, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n <= 0) return QE_OK;
+    if (e->A > 32) return fail(QE_ERR_ARG, "qe_serve_bootstrap supports at most 32 actions");
+    serve_bootstrap_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->T, rows, before, mask_bits, out, n, e->step, use_versions);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_table_export_dense(qe_engine_t* e, float* dense, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    table_export_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(local_table(e), e->S, dense);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_table_import_dense(qe_engine_t* e, const float* dense, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    table_import_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(local_table(e), e->S, dense);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_table_delta_dense(qe_engine_t* e, const float* base, float* delta_out, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    table_delta_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(local_table(e), e->S, base, delta_out);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_table_merge_dense(qe_engine_t* e, float* base_inout, const float* delta_sum, void* stream) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    table_merge_kernel<<<e->sms * 8, 256, 0, (cudaStream_t)stream>>>(local_table(e), e->S, base_inout, delta_sum);
+    e->launches++;
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- environments
 int qe_ttt_reset(uint32_t* boards, int32_t* states_out, uint32_t* mask_bits_out, const uint32_t* uniforms, int32_t slots,
                  uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t n, void* stream) {
@@ -427,6 +506,12 @@ int qe_mdp_reset(int32_t* states, uint32_t* mask_bits_out, int64_t num_states, i
     CK(cudaGetLastError());
     return QE_OK;
 }
+int qe_mdp_masks(const int32_t* states, uint32_t* mask_bits_out, int32_t num_actions, uint32_t env_seed, int32_t n, void* stream) {
+    if (n <= 0) return QE_OK;
+    mdp_masks_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(states, mask_bits_out, num_actions, env_seed, n);
+    CK(cudaGetLastError());
+    return QE_OK;
+}
 int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t num_states, int32_t num_actions,
                 uint32_t env_seed, uint64_t term_threshold, const uint32_t* uniforms, int32_t slots, uint32_t stream_seed,
                 uint32_t t, uint32_t agent0, uint32_t* next_mask_bits, float* rewards, uint8_t* terminated, int32_t n,
@@ -435,6 +520,7 @@ int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t
     if (n <= 0) return QE_OK;
     if (uniforms && slots < 4) return fail(QE_ERR_ARG, "the hash MDP needs 4 uniform slots");
     Uniforms U{uniforms, slots, stream_seed, t, agent0, stream_seed, t};
+    U.ids = e->agent_ids;
     mdp_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(states, actions, (uint32_t)num_states, num_actions, env_seed,
                                                                     term_threshold, U, next_mask_bits, rewards, terminated,
                                                                     e->T.err, n);

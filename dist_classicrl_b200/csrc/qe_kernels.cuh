@@ -51,6 +51,8 @@ struct Table {
     uint32_t* dmask;   // [cap/32] per tile of 32 agents: which agents were deferred (record holds all they wait for)
     uint32_t* smask;   // [cap/32] ... and which need the in-order pass (crowded rows)
     int* err;          // device error flags
+    int hold;          // 1: the TD update publishes values but leaves the table untouched (sharded mode iterates)
+    uint8_t* later_buf; // [cap] hold mode: 1 = a later agent writes the same cell (this one must not commit)
 };
 // writer info words: [0] count, [1] epoch (one u64, atomics), [2] overflow head idx, [3] its epoch (one u64),
 //                    [4 .. 4+inline_cap) entries (agent24 | action << 24)
@@ -417,7 +419,8 @@ __device__ __forceinline__ Scan scan_writers(const Table& T, int* best, bool act
 
 __device__ __forceinline__ void publish_commit(const Table& T, int i, int s, int a, float v, uint32_t later, uint32_t epoch) {
     st_relaxed_u64(T.slot + i, ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(v));
-    if (!later) T.q[(size_t)s * T.ld + a] = v;  // last writer of the cell commits
+    if (T.hold) T.later_buf[i] = (uint8_t)later;
+    else if (!later) T.q[(size_t)s * T.ld + a] = v;  // last writer of the cell commits
 }
 
 // Deferred record (32 bytes per agent, written by the first pass for agents that have to wait for someone)
@@ -892,15 +895,81 @@ __global__ void gather_rows_kernel(Table T, const int32_t* __restrict__ states, 
     }
 }
 
-__global__ void table_fill_kernel(Table T, int64_t S, float value, uint32_t seed, int random) {
+__global__ void table_fill_kernel(Table T, int64_t S, float value, uint32_t seed, int random, uint64_t state_base) {
     const size_t total = (size_t)S * T.ld;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
         const int a = (int)(x % T.ld);
-        const size_t s = x / T.ld;
+        const size_t s = x / T.ld + state_base;  // global state id: a shard fills exactly its slice of the whole table
         float v = 0.0f;
         if (a < T.A) v = random ? (float)(fmix32((uint32_t)(s * (size_t)T.A + a) ^ (seed * kGold)) >> 8) * 5.9604644775390625e-08f : value;
         T.q[x] = v;
+    }
+}
+
+// ------------------------------------------------------------------ sharded / replicated table helpers
+// commit of a held TD update: the last writer of every cell stores its published value
+__global__ void learn_commit_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !T.later_buf[i]) T.q[(size_t)states[i] * T.ld + actions[i]] = __uint_as_float((uint32_t)ld_relaxed_u64(T.slot + i));
+}
+// Bootstrap requests of agents that live on another shard: m = max over the legal actions of the value of
+// (row, a') just before an agent that sorts before local agent `pos` (all local agents < pos are earlier, all others
+// later).  Values of earlier writers come from their published slots (the held update of this epoch), everything
+// else from the untouched table.  use_versions = 0: plain snapshot max.
+__global__ void serve_bootstrap_kernel(Table T, const int32_t* __restrict__ rows, const int32_t* __restrict__ pos,
+                                       const uint32_t* __restrict__ masks, float* __restrict__ out, int n, uint32_t epoch,
+                                       int use_versions) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int row = rows[r], before = pos[r];
+    const uint32_t full = T.A >= 32 ? 0xFFFFFFFFu : ((1u << T.A) - 1u);
+    const uint32_t legal = masks ? (masks[r] & full) : full;
+    RowWriters w = load_writers(T, row, epoch);
+    if (!use_versions) w.count = 0;
+    float m = -INFINITY;
+    for (uint32_t b = legal; b; b &= b - 1u) {
+        const int a2 = __ffs(b) - 1;
+        int best = -1;
+        for_each_writer(T, w, [&](uint32_t e) {
+            const int j = (int)(e & kNone);
+            if ((int)(e >> 24) == a2 && j < before) best = max(best, j);
+        });
+        const float v = best >= 0 ? __uint_as_float((uint32_t)ld_relaxed_u64(T.slot + best)) : __ldcg(T.q + (size_t)row * T.ld + a2);
+        m = fmax_plain(m, v);
+    }
+    out[r] = m;
+}
+// replicated table: delta[s][a] = Q[s][a] - base[s][a]   (dense [S][A] buffers)
+__global__ void table_delta_kernel(Table T, int64_t S, const float* __restrict__ base, float* __restrict__ delta) {
+    const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
+        const size_t s = x / T.A;
+        delta[x] = __fsub_rn(T.q[s * T.ld + (x - s * T.A)], base[x]);
+    }
+}
+// ... and Q = base = base + sum of the ranks' deltas
+__global__ void table_merge_kernel(Table T, int64_t S, float* __restrict__ base, const float* __restrict__ delta_sum) {
+    const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
+        const size_t s = x / T.A;
+        const float v = __fadd_rn(base[x], delta_sum[x]);
+        base[x] = v;
+        T.q[s * T.ld + (x - s * T.A)] = v;
+    }
+}
+__global__ void table_export_kernel(Table T, int64_t S, float* __restrict__ dense) {
+    const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
+        const size_t s = x / T.A;
+        dense[x] = T.q[s * T.ld + (x - s * T.A)];
+    }
+}
+__global__ void table_import_kernel(Table T, int64_t S, const float* __restrict__ dense) {
+    const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
+        const size_t s = x / T.A;
+        T.q[s * T.ld + (x - s * T.A)] = dense[x];
     }
 }
 
@@ -952,6 +1021,11 @@ __global__ void mdp_step_kernel(int32_t* __restrict__ states, const int32_t* __r
     if (next_masks) next_masks[i] = mdp_mask((uint32_t)s, A, env_seed);
     rewards[i] = r;
     terminated[i] = term;
+}
+
+__global__ void mdp_masks_kernel(const int32_t* __restrict__ states, uint32_t* __restrict__ masks, int A, uint32_t env_seed, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) masks[i] = mdp_mask((uint32_t)states[i], A, env_seed);
 }
 
 // ------------------------------------------------------------------ fused persistent loop

@@ -77,6 +77,7 @@ class DeviceVecEnv(DistClassicRLEnv):
         self.output = output
         self._rng = CounterRNG(seed)
         self._resets = 0
+        self.agent0 = 0  # global index of this environment's first agent in the uniform stream (replicated multi-GPU mode)
         n = self.num_envs
         self.states = torch.zeros(n, dtype=torch.int32, device=self.device)
         self.states_scratch = torch.zeros(n, dtype=torch.int32, device=self.device)

@@ -36,7 +36,7 @@ class HashMDPVecEnv(DeviceVecEnv):
 
     def _reset_kernel(self, u_ptr, slots, seed, t) -> None:
         capi.check(self._lib.qe_mdp_reset(self.states.data_ptr(), self.mask_bits.data_ptr(), self.num_states, self.num_actions,
-                                          self.env_seed, u_ptr, slots, seed, t, 0, self.num_envs, self._stream()))
+                                          self.env_seed, u_ptr, slots, seed, t, self.agent0, self.num_envs, self._stream()))
 
     def step(self, actions):
         torch = _torch()
@@ -47,7 +47,7 @@ class HashMDPVecEnv(DeviceVecEnv):
         rewards = torch.empty(n, dtype=torch.float32, device=self.device)
         term = torch.empty(n, dtype=torch.uint8, device=self.device)
         capi.check(self._lib.qe_mdp_step(self._err_handle(), self.states.data_ptr(), act.data_ptr(), self.num_states,
-                                         self.num_actions, self.env_seed, self.term_threshold, u_ptr, slots, seed, t, 0,
+                                         self.num_actions, self.env_seed, self.term_threshold, u_ptr, slots, seed, t, self.agent0,
                                          self.mask_bits.data_ptr(), rewards.data_ptr(), term.data_ptr(), n, self._stream()))
         capi.check(self._lib.qe_sync(self._err_handle(), self._stream()))
         return self._finish_step(rewards, term)

@@ -31,7 +31,7 @@ class TicTacToeVecEnv(DeviceVecEnv):
 
     def _reset_kernel(self, u_ptr, slots, seed, t) -> None:
         capi.check(self._lib.qe_ttt_reset(self.env_words.data_ptr(), self.states.data_ptr(), self.mask_bits.data_ptr(), u_ptr,
-                                          slots, seed, t, 0, self.num_envs, self._stream()))
+                                          slots, seed, t, self.agent0, self.num_envs, self._stream()))
 
     def step(self, actions):
         torch = _torch()
@@ -41,7 +41,7 @@ class TicTacToeVecEnv(DeviceVecEnv):
         act = self._actions_dev(actions)
         rewards = torch.empty(n, dtype=torch.float32, device=self.device)
         term = torch.empty(n, dtype=torch.uint8, device=self.device)
-        capi.check(self._lib.qe_ttt_step(self._err_handle(), self.env_words.data_ptr(), act.data_ptr(), u_ptr, slots, seed, t, 0,
+        capi.check(self._lib.qe_ttt_step(self._err_handle(), self.env_words.data_ptr(), act.data_ptr(), u_ptr, slots, seed, t, self.agent0,
                                          self.states.data_ptr(), self.mask_bits.data_ptr(), rewards.data_ptr(),
                                          term.data_ptr(), n, self._stream()))
         capi.check(self._lib.qe_sync(self._err_handle(), self._stream()))  # raises AssertionError("Invalid move.")

@@ -99,6 +99,8 @@ int qe_ttt_step(qe_engine_t* e, uint32_t* boards, const int32_t* actions, const 
 int qe_mdp_reset(int32_t* states, uint32_t* mask_bits_out, int64_t num_states, int32_t num_actions, uint32_t env_seed,
                  const uint32_t* uniforms, int32_t slots, uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t n,
                  void* stream);
+/* legal-action bits of the given states (a pure function of the state) */
+int qe_mdp_masks(const int32_t* states, uint32_t* mask_bits_out, int32_t num_actions, uint32_t env_seed, int32_t n, void* stream);
 int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t num_states, int32_t num_actions,
                 uint32_t env_seed, uint64_t term_threshold, const uint32_t* uniforms, int32_t slots, uint32_t stream_seed,
                 uint32_t t, uint32_t agent0, uint32_t* next_mask_bits, float* rewards, uint8_t* terminated, int32_t n,
@@ -140,6 +142,29 @@ typedef struct {
 } qe_run_t;
 
 int qe_fused_steps(qe_engine_t* e, const qe_agents_t* agents, const qe_run_t* run, void* stream);
+
+/* ---- multi-GPU support (new relative to the reference, whose MPI trainer keeps ONE table on rank 0,
+ *      q_learning_async_dist.py:59-281) ------------------------------------------------------------------------
+ * Sharded table: a handle created with num_states = S_local owns the global states [first_state, first_state +
+ * S_local); every state id passed to qe_select / qe_learn / qe_gather / qe_serve_bootstrap is then a GLOBAL id. */
+int qe_set_state_base(qe_engine_t* e, int64_t first_state);
+/* global ids of the local agents for the counter stream U[t][id][k] (device uint32[N], NULL = agent0 + i); used by
+ * qe_select and qe_mdp_step */
+int qe_set_agent_ids(qe_engine_t* e, const uint32_t* ids);
+/* hold = 1: qe_learn (sequential mode) publishes every agent's new value but leaves the table untouched, so the
+ * update can be repeated with better bootstrap values of remote states; qe_learn_commit applies the last one. */
+int qe_set_hold(qe_engine_t* e, int32_t hold);
+int qe_learn_commit(qe_engine_t* e, const int32_t* states, const int32_t* actions, int32_t n, void* stream);
+/* bootstrap requests of agents living on another shard: out[r] = max over mask_bits[r] of the value of
+ * (rows[r], a') just before an agent that sorts after exactly the first before[r] local agents of the last held
+ * qe_learn (use_versions = 0: plain table max) */
+int qe_serve_bootstrap(qe_engine_t* e, const int32_t* rows, const int32_t* before, const uint32_t* mask_bits, float* out,
+                       int32_t n, int32_t use_versions, void* stream);
+/* Replicated table: dense [S][A] device buffers; delta = Q - base, then Q = base = base + sum_of_deltas */
+int qe_table_export_dense(qe_engine_t* e, float* dense, void* stream);
+int qe_table_import_dense(qe_engine_t* e, const float* dense, void* stream);
+int qe_table_delta_dense(qe_engine_t* e, const float* base, float* delta_out, void* stream);
+int qe_table_merge_dense(qe_engine_t* e, float* base_inout, const float* delta_sum, void* stream);
 
 /* introspection for benchmarks / tests */
 uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k);
