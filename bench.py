@@ -5,11 +5,13 @@
 
 One "step" = one vector step of all agents (N_agents agent-steps).  Metric: agent-steps/s (BASELINE.json).
 Workload at --gpus 1: BASELINE config 3 -- hash MDP, 1 000 000 states x 16 actions, 2^20 agents, masked actions,
-eps 0.1, lr 0.1, gamma 0.99, uniform[0,1) initial table, on-device counter stream.  With --gpus N > 1 (torchrun)
-the state-range-sharded table of config 4 (100 M states x 8 actions, 2^22 agents in total).
+eps 0.1, lr 0.1, gamma 0.99, uniform[0,1) initial table, on-device counter stream.  With --gpus N > 1 (torchrun,
+one rank per GPU) every GPU runs that workload on its own replica of the table and the replicas are merged by a
+Q-delta all-reduce every 8 vector steps (config 5; weak scaling); a bounded run of the state-range-sharded table of
+config 4 (100 M states x 8 actions, 2^22 agents in total) is reported beside it under `sharded_c4`.
 
 Prints ONE JSON line (see the contract in the task description): `value` = device-resident throughput
-(CUDA events around the engine's kernel launches, L2 flushed between timed steps), `e2e` = the same metric
+(CUDA events around the K timed steps, 8 vector steps per fused launch; the working set is larger than L2), `e2e` = the same metric
 through the reference-shaped public API (`SingleThreadQLearning.run_steps`) with the step's pre-drawn uniforms
 copied host->device from pinned memory and the step's results copied back, `roofline` (HBM), `cpu_baseline`
 (C port of the reference loop on the host cores), `clocks`, `gpu_launches`.
@@ -154,7 +156,7 @@ def run_reference(args) -> dict:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         sys.exit(0)
-    workload = args.workload or ("c3" if args.gpus == 1 else "c4")
+    workload = args.workload or "c3"
     s, a, n, desc = WORKLOADS[workload]
     # bounded sample: the reference loop is sequential in the agents, so per-agent-step cost does not depend on
     # the batch size; cap the agents so that warm-up + K steps stay within a few minutes
@@ -166,8 +168,8 @@ def run_reference(args) -> dict:
     return {
         "impl": "reference", "metric": "agent-steps/s", "value": rate, "unit": "agent-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload}: {desc}", "states": s, "actions": a, "agents": n, "sample_agents": agents,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{workload}: {desc}", "states": s, "actions": a, "agents_per_gpu": n, "agents": n * args.gpus, "sample_agents": agents,
                    "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM},
         "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -175,11 +177,18 @@ def run_reference(args) -> dict:
     }
 
 
-# --------------------------------------------------------------------------------------------- our arm, 1 GPU
-def run_single_gpu(args) -> dict:
+# --------------------------------------------------------------------------------------------- our arm
+SYNC_EVERY = 8  # vector steps per fused launch; with N > 1 GPUs also the period of the Q-delta all-reduce
+
+
+def run_ours(args) -> dict | None:
+    """N = 1: BASELINE config 3 on one GPU.  N > 1 (torchrun, one rank per GPU): the same workload on EVERY GPU with a
+    replicated table merged by a Q-delta all-reduce every SYNC_EVERY steps (config 5, weak scaling), plus a bounded
+    run of the state-range-sharded 100M-state table (config 4) reported under `sharded_c4`."""
     import torch
 
     from dist_classicrl_b200 import capi
+    from dist_classicrl_b200 import distributed as D
     from dist_classicrl_b200.algorithms.base_algorithms.q_learning_optimal import OptimalQLearningBase
     from dist_classicrl_b200.algorithms.runtime import SingleThreadQLearning
     from dist_classicrl_b200.environments import HashMDPVecEnv, TicTacToeVecEnv
@@ -188,119 +197,188 @@ def run_single_gpu(args) -> dict:
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    tp = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+        tp = D.TorchDistTransport()
     workload = args.workload or "c3"
     s, a, n, desc = WORKLOADS[workload]
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
     lib = capi.lib()
     K, W = args.steps, max(3, args.warmup)
+    stream = torch.cuda.current_stream()
 
-    def make(seed_offset=0):
-        algo = OptimalQLearningBase(s, a, GAMMA, seed=STREAM_SEED + seed_offset)
+    def sync_all():
+        torch.cuda.synchronize()
+        if tp is not None:
+            tp.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if tp is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if tp is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+        return float(t.item())
+
+    def make():
+        algo = OptimalQLearningBase(s, a, GAMMA, seed=STREAM_SEED, device=local)
         if workload == "c2":
-            env = TicTacToeVecEnv(n, seed=STREAM_SEED + seed_offset, output="torch")
+            env = TicTacToeVecEnv(n, seed=STREAM_SEED, device=local, output="torch")
         else:
             algo.fill_random(TABLE_SEED)
-            env = HashMDPVecEnv(n, s, a, env_seed=ENV_SEED, p_term=P_TERM, seed=STREAM_SEED + seed_offset, output="torch")
+            env = HashMDPVecEnv(n, s, a, env_seed=ENV_SEED, p_term=P_TERM, seed=STREAM_SEED, device=local, output="torch")
+        env.agent0 = rank * n  # every GPU drives its own agents (global agent ids rank*n ...)
         env.attach(algo)
         env.reset()
         return algo, env
 
-    # ---------------- device-resident throughput: one launch per vector step, L2 flushed in between
+    # ---------------- device-resident throughput: SYNC_EVERY vector steps per launch (+ table merge when N > 1)
     algo, env = make()
     ep_ret = torch.zeros(n, dtype=torch.float32, device=dev)
     ag = env.agents_struct(ep_ret)
-    thresh = np.full(1, explore_threshold(EPS), dtype=np.uint64)
-    lrs = np.full(1, LR, dtype=np.float32)
-    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    stats = torch.zeros(1, dtype=torch.float64, device=dev)
     ep_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
+    rt0 = SingleThreadQLearning(algo, ConstantSchedule(LR), ConstantSchedule(EPS))
+    rep = D.ReplicatedQLearning(rt0, tp, sync_every=SYNC_EVERY) if tp is not None else None
+    t_next = [0]
 
-    def launch(t):
+    def launch(k):
+        th = np.full(k, explore_threshold(EPS), dtype=np.uint64)
+        lrs = np.full(k, LR, dtype=np.float32)
         run = capi.QeRun()
-        run.steps = 1
-        run.explore_thresholds_host = thresh.ctypes.data_as(C.c_void_p)
+        run.steps = k
+        run.explore_thresholds_host = th.ctypes.data_as(C.c_void_p)
         run.learning_rates_host = lrs.ctypes.data_as(C.c_void_p)
         run.slots = env.slots
         run.stream_seed = run.env_stream_seed = STREAM_SEED
-        run.t0 = run.env_t0 = t
+        run.t0 = run.env_t0 = t_next[0]
+        run.agent0 = env.agent0
         run.use_masks = 1
         run.empty_all = int(a > 10)
         run.episode_sum, run.episode_count = stats.data_ptr(), ep_cnt.data_ptr()
         capi.check(lib.qe_fused_steps(algo.handle, C.byref(ag), C.byref(run), C.c_void_p(stream.cuda_stream)))
+        t_next[0] += k
 
-    for t in range(W):
-        launch(t)
+    def chunks(total):
+        out, left = [], total
+        while left > 0:
+            out.append(min(SYNC_EVERY, left))
+            left -= out[-1]
+        return out
+
+    for k in chunks(W):
+        launch(k)
+        if rep is not None:
+            rep.sync()
     capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     launches0 = lib.qe_kernel_launches(algo.handle)
-    events = []
-    for k in range(K):
-        flush.fill_(k & 0xFF)  # evict the table from L2 between timed steps
+    kernel_events = []
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_begin.record(stream)
+    for k in chunks(K):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        launch(W + k)
+        launch(k)
         e1.record(stream)
-        events.append((e0, e1))
-    torch.cuda.synchronize()
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in events]
+        kernel_events.append((k, e0, e1))
+        if rep is not None:
+            rep.sync()
+    e_end.record(stream)
+    sync_all()
     capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
+    total_ms = max_over_ranks(e_begin.elapsed_time(e_end))
+    kernel_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in kernel_events)
     gpu_launches = int(lib.qe_kernel_launches(algo.handle) - launches0)
-    total_ms = sum(step_ms)
-    value = n * K / (total_ms * 1e-3)
-
-    # ---------------- steady state: K steps in ONE persistent launch (table stays L2-resident, no flush)
-    th_k, lr_k = np.full(K, explore_threshold(EPS), dtype=np.uint64), np.full(K, LR, dtype=np.float32)
-    run = capi.QeRun()
-    run.steps = K
-    run.explore_thresholds_host, run.learning_rates_host = th_k.ctypes.data_as(C.c_void_p), lr_k.ctypes.data_as(C.c_void_p)
-    run.slots = env.slots
-    run.stream_seed = run.env_stream_seed = STREAM_SEED
-    run.t0 = run.env_t0 = W + K
-    run.use_masks, run.empty_all = 1, int(a > 10)
-    run.episode_sum, run.episode_count = stats.data_ptr(), ep_cnt.data_ptr()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    capi.check(lib.qe_fused_steps(algo.handle, C.byref(ag), C.byref(run), C.c_void_p(stream.cuda_stream)))
-    e1.record(stream)
-    torch.cuda.synchronize()
-    capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
-    steady_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    value = world * n * K / (total_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
     grid_blocks = int(lib.qe_fused_grid_blocks(algo.handle))
-    del algo, env
+    buf = (C.c_uint64 * 33)()
+    m = lib.qe_fused_phase_ns(algo.handle, buf, 33)
+    phases = None
+    if m >= 4:
+        ks = (m - 1) // 3
+        phases = {name: sum(buf[1 + ph + 3 * j] - buf[ph + 3 * j] for j in range(ks)) / ks / 1e3
+                  for ph, name in enumerate(("select_step_register_us", "td_first_pass_us", "td_deferred_us"))}
+    episodes = int(sum_over_ranks(float(ep_cnt.item())))
+    del algo, env, rep, rt0
 
     # ---------------- e2e through the public API: per step H2D of that step's uniforms (pinned) + D2H of the results
     algo, env = make()
     rt = SingleThreadQLearning(algo, ConstantSchedule(LR), ConstantSchedule(EPS))
     rt.history_mode = "summary"
+    runner = D.ReplicatedQLearning(rt, tp, sync_every=1) if tp is not None else rt
     Ke = min(K, 20)
     slots = env.slots
     u_host = torch.empty((W + Ke, n, slots), dtype=torch.int32).pin_memory()
-    u_host.numpy().view(np.uint32)[:] = draw_uniforms(STREAM_SEED, 0, W + Ke, n, slots)
+    u_host.numpy().view(np.uint32)[:] = draw_uniforms(STREAM_SEED, 0, W + Ke, n, slots, agent0=env.agent0)
     pre = PredrawnUniforms(u_host.numpy().view(np.uint32))  # no copy: already contiguous uint32 (pinned)
     algo._rng = env._rng = pre
     sd = {"states": None, "infos": {}, "rewards": np.zeros(n, dtype=np.float32)}
     for _ in range(W):
-        _, _, _, sd = rt.run_steps(1, env, sd)
-    torch.cuda.synchronize()
+        _, _, _, sd = runner.run_steps(1, env, sd)
+    sync_all()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        _, _, _, sd = rt.run_steps(1, env, sd)  # returns host copies of the agents' running returns
+        _, _, _, sd = runner.run_steps(1, env, sd)  # returns host copies of the agents' running returns
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d = n * slots * 4 + 12
     d2h = n * 4 + 16 + 4
-    e2e = {"value": n * Ke / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": Ke, "api": "SingleThreadQLearning.run_steps(1, env, state_dict) with PredrawnUniforms in pinned host memory"}
+    e2e = {"value": world * n * Ke / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+           "steps": Ke, "api": ("ReplicatedQLearning(sync_every=1)." if tp is not None else "SingleThreadQLearning.") +
+           "run_steps(1, env, state_dict) with PredrawnUniforms in pinned host memory; host copy of the running returns every step"}
+    del algo, env, runner, rt
 
-    # ---------------- roofline + CPU baseline
+    # ---------------- sharded 100M-state table (config 4), bounded
+    sharded = None
+    if tp is not None and not args.no_sharded:
+        s4, a4, n4, desc4 = WORKLOADS["c4"]
+        sh = D.ShardedQLearning(s4, a4, GAMMA, n4, tp, env_seed=ENV_SEED, p_term=P_TERM, seed=STREAM_SEED, device=local)
+        sh.fill_random(TABLE_SEED)
+        sh.reset()
+        eps_s, lr_s = ConstantSchedule(EPS), ConstantSchedule(LR)
+        sh.run_steps(3, eps_s, lr_s)
+        sync_all()
+        r0 = sh.rounds_total
+        ks = min(K, 10)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        sh.run_steps(ks, eps_s, lr_s)
+        b1.record(stream)
+        sync_all()
+        ms = max_over_ranks(b0.elapsed_time(b1))
+        sharded = {"workload": f"c4: {desc4}", "value": n4 * ks / (ms * 1e-3), "unit": "agent-steps/s", "scaling": "strong", "steps": ks,
+                   "ms_per_step": ms / ks, "fixed_point_rounds_per_step": (sh.rounds_total - r0) / ks,
+                   "states": s4, "actions": a4, "agents": n4,
+                   "exchange": "NCCL all-to-all: bootstrap requests + answers per round, agent migration per step"}
+        del sh
+
+    if rank != 0:
+        return None
+    # ---------------- roofline + CPU baseline (rank 0)
     peak, peak_src = measured_peak()
     balg = alg_bytes(a)
-    achieved = n * balg / (total_ms / K * 1e-3) / 1e9
+    per_launch_ms = kernel_ms / len(kernel_events)
+    steps_per_launch = K / len(kernel_events)
+    achieved = n * steps_per_launch * balg / (per_launch_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -308,32 +386,40 @@ def run_single_gpu(args) -> dict:
             traffic = json.load(open(tpath)).get(workload)
         except Exception:  # noqa: BLE001
             traffic = None
+    kname = "fused_kernel<MDP,2>" if workload != "c2" else "fused_kernel<TTT,2>"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "fused_kernel<MDP,4>" if workload != "c2" else "fused_kernel<TTT,4>",
-                "algorithmic_bytes_per_agent_step": balg,
-                "steady_state_frac": n * K * balg / (steady_ms * 1e-3) / 1e9 / peak}
-    cpu_agents = n if workload == "c2" else 1 << 20
-    cpu_steps = 2000 if workload == "c2" else 12
-    cpu_rate, cpu_dt = cpu_port_rate(workload, cpu_agents, cpu_steps)
-    py_agents, py_steps = (n, 50) if workload == "c2" else (1 << 13, 4)
-    py_rate = python_port_rate(workload, py_agents, py_steps)
-    cpu_baseline = {"value": cpu_rate, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
-                    "sample": f"{cpu_steps} vector steps x {cpu_agents} agents, C port of the reference loop ({cpu_dt:.1f} s)",
-                    "python_port_value": py_rate, "python_port_cores": 1,
-                    "python_port_sample": f"{py_steps} vector steps x {py_agents} agents, NumPy/Python restatement (per-agent Python learn loop like the reference)"}
-    return {
-        "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+                "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_agent_step": balg,
+                "algorithmic_bytes_per_launch": n * steps_per_launch * balg, "avg_launch_ms": per_launch_ms,
+                "steps_per_launch": steps_per_launch, "phase_us_per_step": phases}
+    cpu_baseline = None
+    if world == 1:
+        cpu_agents = n if workload == "c2" else 1 << 20
+        cpu_steps = 2000 if workload == "c2" else 12
+        cpu_rate, cpu_dt = cpu_port_rate(workload, cpu_agents, cpu_steps)
+        py_agents, py_steps = (n, 50) if workload == "c2" else (1 << 13, 4)
+        py_rate = python_port_rate(workload, py_agents, py_steps)
+        cpu_baseline = {"value": cpu_rate, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"{cpu_steps} vector steps x {cpu_agents} agents, C port of the reference loop ({cpu_dt:.1f} s)",
+                        "python_port_value": py_rate, "python_port_cores": 1,
+                        "python_port_sample": f"{py_steps} vector steps x {py_agents} agents, NumPy/Python restatement (per-agent Python learn loop like the reference)"}
+    cfg = {"workload": f"{workload}: {desc}" + (f", one replica per GPU, Q-delta all-reduce every {SYNC_EVERY} steps (BASELINE config 5)" if world > 1 else ""),
+           "states": s, "actions": a, "agents_per_gpu": n, "agents": n * world, "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM,
+           "table_init": "uniform[0,1)" if workload != "c2" else "zeros", "rng": "on-device counter stream",
+           "steps_per_launch": SYNC_EVERY,
+           "timing": "CUDA events around the K timed steps (max over ranks); no L2 flush: the working set (256 MB of row blocks + "
+                     "~60 MB of per-agent arrays) is larger than the 126 MB L2",
+           "grid_blocks": grid_blocks}
+    out = {
+        "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"{workload}: {desc}", "states": s, "actions": a, "agents": n, "eps": EPS, "lr": LR, "gamma": GAMMA,
-                   "p_term": P_TERM, "table_init": "uniform[0,1)" if workload != "c2" else "zeros", "rng": "on-device counter stream",
-                   "timing": "CUDA events around each step's launch; L2 flushed (256 MiB write) between timed steps",
-                   "steady_state_value": n * K / (steady_ms * 1e-3), "steady_state_ms_per_step": steady_ms / K,
-                   "steady_state_note": "same K steps in ONE persistent launch, table L2-resident, no flush",
-                   "grid_blocks": grid_blocks},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
-        "episodes": int(ep_cnt.item()),
+        "data": "synthetic", "config": cfg, "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+        "episodes": episodes,
     }
+    if cpu_baseline is not None:
+        out["cpu_baseline"] = cpu_baseline
+    if sharded is not None:
+        out["sharded_c4"] = sharded
+    return out
 
 
 def main() -> None:
@@ -343,17 +429,23 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the bounded run of the sharded 100M-state table")
     args = ap.parse_args()
     if args.impl == "reference":
         out = run_reference(args)
-    elif args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        from dist_classicrl_b200.distributed import bench_sharded
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus > 1 and world == 1:
+            raise SystemExit(f"--gpus {args.gpus} needs one rank per GPU: launch with python -m torch.distributed.run "
+                             f"--nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
+        out = run_ours(args)
+        if world > 1:
+            import torch.distributed as dist
 
-        out = bench_sharded(args)
+            dist.barrier()
+            dist.destroy_process_group()
         if out is None:
             return
-    else:
-        out = run_single_gpu(args)
     print(json.dumps(out))
 
 

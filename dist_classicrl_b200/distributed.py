@@ -479,7 +479,6 @@ class ReplicatedQLearning:
         lib, h = capi.lib(), self.algorithm.handle
         self.algorithm._before_device_op()
         capi.check(lib.qe_table_delta_dense(h, self.base.data_ptr(), self.delta.data_ptr(), self._stream()))
-        _torch().cuda.current_stream().synchronize()
         self.tp.all_reduce_sum_(self.delta)
         capi.check(lib.qe_table_merge_dense(h, self.base.data_ptr(), self.delta.data_ptr(), self._stream()))
         self.algorithm._device_wrote()
