@@ -190,6 +190,12 @@ class OptimalQLearningBase:
     def save(self, filename: str) -> None:
         np.save(filename, self.q_table)
 
+    def load(self, filename: str) -> None:
+        """Resume from a table written by :meth:`save` (or by the reference's ``save``, QLO:252-261); an fp64 table
+        of the reference is rounded to fp32."""
+        name = filename if str(filename).endswith(".npy") else f"{filename}.npy"
+        self.q_table = np.load(name)
+
     # ------------------------------------------------------------------ select
     def _variant(self, n: int, deterministic: bool, masked: bool) -> str:
         """Dispatcher branch of QLO:671-726 (decides RNG method names and the empty-mask behaviour)."""

@@ -128,7 +128,34 @@ class BaseRuntime(ABC):
             return self.algorithm.choose_actions(obs, exploration_rate=0.0, deterministic=True)
         return self.algorithm.choose_actions(states=obs, action_masks=masks, exploration_rate=0.0, deterministic=True)
 
+    def _evaluate_fused(self, env, steps: int | None, episodes: int | None):
+        """Evaluation on the device: greedy select + env step in the fused loop, table untouched."""
+        n = env.num_envs
+        agent_rewards = np.zeros(n, dtype=np.float32)
+        history: list[float] = []
+        saved = self.history_mode
+        self.history_mode = "full"
+        try:
+            if steps is not None:
+                vector_steps = len(range(0, steps, n))
+                if vector_steps:
+                    history = self._run_fused(env, vector_steps, agent_rewards, evaluate=True)
+            else:
+                while len(history) < episodes:  # whole vector steps, like BRT:375-383: stop after the step that reaches the count
+                    trace: dict = {}
+                    self._run_fused(env, 16, agent_rewards, evaluate=True, trace=trace, history_rows=True)
+                    for row in trace["episode_rows"]:
+                        history.extend(row)
+                        if len(history) >= episodes:
+                            break
+        finally:
+            self.history_mode = saved
+        return sum(history), history
+
     def evaluate_steps(self, env, steps: int):
+        if self._can_fuse(env) and not isinstance(self.algorithm._rng, PredrawnUniforms):
+            env.reset(seed=42)
+            return self._evaluate_fused(env, steps, None)
         states, _ = env.reset(seed=42)
         n_agents = len(_split(states)[0])
         agent_rewards = np.zeros(n_agents, dtype=np.float32)
@@ -140,6 +167,9 @@ class BaseRuntime(ABC):
         return sum(reward_history), reward_history
 
     def evaluate_episodes(self, env, episodes: int):
+        if self._can_fuse(env) and not isinstance(self.algorithm._rng, PredrawnUniforms):
+            env.reset(seed=42)
+            return self._evaluate_fused(env, None, episodes)
         states, _ = env.reset(seed=42)
         n_agents = len(_split(states)[0])
         agent_rewards = np.zeros(n_agents, dtype=np.float32)
@@ -163,7 +193,8 @@ class BaseRuntime(ABC):
             return False
         return algo.action_size <= 32 and env.num_actions == algo.action_size and env.num_states == algo.state_size
 
-    def _run_fused(self, env, steps: int, agent_rewards, *, trace: dict | None = None) -> list[float]:
+    def _run_fused(self, env, steps: int, agent_rewards, *, trace: dict | None = None, evaluate: bool = False,
+                   history_rows: bool = False) -> list[float]:
         """K vector steps in ``qe_fused_steps`` launches; returns the episode-reward history (agent order
         within a step, steps in order -- BRT:218-221)."""
         import torch
@@ -190,12 +221,16 @@ class BaseRuntime(ABC):
             th = np.empty(k, dtype=np.uint64)
             lrs = np.empty(k, dtype=np.float32)
             for j in range(k):  # BRT:245-263: values read before the update of the same step
+                if evaluate:  # deterministic=True, exploration_rate=0.0 (BRT:319-328); schedules untouched
+                    th[j], lrs[j] = 0, 0.0
+                    continue
                 th[j] = explore_threshold(self.exploration_rate_schedule.get_value())
                 lrs[j] = np.float32(self.lr_schedule.get_value())
                 self.lr_schedule.update(n)
                 self.exploration_rate_schedule.update(n)
             run = capi.QeRun()
             run.steps = k
+            run.evaluate = int(evaluate)
             run.explore_thresholds_host = th.ctypes.data_as(C.c_void_p)
             run.learning_rates_host = lrs.ctypes.data_as(C.c_void_p)
             u_dev = None
@@ -237,10 +272,14 @@ class BaseRuntime(ABC):
             if full:
                 flat = tr_ep.reshape(-1)
                 history.extend(flat[~torch.isnan(flat)].cpu().tolist())
+                if history_rows and trace is not None:
+                    host = tr_ep.cpu().numpy()
+                    trace.setdefault("episode_rows", []).extend(row[~np.isnan(row)].tolist() for row in host)
             for name, buf in keep:
                 trace.setdefault(name, []).append(buf.cpu().numpy())
             done += k
-        algo._device_wrote()
+        if not evaluate:
+            algo._device_wrote()
         env.refresh_after_fused()
         self.last_episode_count = int(ep_cnt.item())
         self.last_episode_sum = float(ep_sum.item())

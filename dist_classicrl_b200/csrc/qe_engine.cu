@@ -596,9 +596,10 @@ int qe_fused_steps(qe_engine_t* e, const qe_agents_t* ag, const qe_run_t* run, v
     F.trace_next = run->trace_next_states; F.trace_epret = run->trace_episode_returns;
     F.ep_sum = run->episode_sum; F.ep_count = run->episode_count;
     F.phase_ns = e->phase_ns;
+    F.evaluate = run->evaluate != 0;
     e->phase_steps = run->steps < 10 ? run->steps : 10;
     if ((F.ep_sum == nullptr) != (F.ep_count == nullptr)) return fail(QE_ERR_ARG, "episode_sum and episode_count go together");
-    e->step += (uint32_t)run->steps;
+    if (!F.evaluate) e->step += (uint32_t)run->steps;
     switch (ag->env_kind) {
         case QE_ENV_MDP: return launch_fused_env<0>(e, F, st);
         case QE_ENV_TTT: return launch_fused_env<1>(e, F, st);

@@ -1056,6 +1056,7 @@ struct FusedArgs {
     float* trace_epret;
     double* ep_sum;
     unsigned long long* ep_count;
+    int evaluate;                // 1: no TD update (evaluation loops, BRT:293-384): select + env step only
     uint64_t* phase_ns;          // optional [31]: %globaltimer at launch and after each of the 3 phases of the first 10 steps
 };
 
@@ -1103,8 +1104,10 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
                 s = cur[i];
                 // register as a writer of row s right away: the ticket travels while the row is fetched
                 info = reinterpret_cast<unsigned long long*>(row_info(T, s));
-                atomicMax(info, (unsigned long long)epoch << 32);  // a stale (older-epoch) counter restarts at {epoch, 0}
-                ticket = (uint32_t)atomicAdd(info, 1ull);
+                if (!F.evaluate) {
+                    atomicMax(info, (unsigned long long)epoch << 32);  // a stale (older-epoch) counter restarts at {epoch, 0}
+                    ticket = (uint32_t)atomicAdd(info, 1ull);
+                }
                 if (ENV != 0) ew = F.envw[i];
                 valid = F.use_masks ? env_mask<ENV>(s, ew, T.A, F.env_seed) : full;
                 explore = (uint64_t)U.draw(i, 0) < thresh;
@@ -1135,7 +1138,8 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
                     s2 = 0;
                 }
                 // writer entry {agent, action}: inline in the row block, overflow -> list through node[]
-                if (ticket < (uint32_t)T.inline_cap) {
+                if (F.evaluate) {
+                } else if (ticket < (uint32_t)T.inline_cap) {
                     reinterpret_cast<uint32_t*>(info)[4 + ticket] = (uint32_t)i | ((uint32_t)a << 24);
                 } else {
                     const unsigned long long old = atomicExch(info + 1, ((unsigned long long)epoch << 32) | (unsigned long long)i);
@@ -1175,6 +1179,7 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
         }
         grid.sync();
         if (clk && k < 10) F.phase_ns[1 + 3 * k] = global_ns();
+        if (F.evaluate) continue;  // the table is read-only: nothing to update, the barrier above orders the state buffers
 
         // ---------------- phase B1: exact sequential TD update, first pass (agents that wait for nobody finish)
         for (int base = (tid & ~31); base < n; base += nthreads) {

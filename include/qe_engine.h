@@ -139,6 +139,9 @@ typedef struct {
     /* optional statistics (device scalars, accumulated): sum / count of finished-episode returns */
     double* episode_sum;
     unsigned long long* episode_count;
+    /* 1: evaluation loop (BaseRuntime.evaluate_steps / evaluate_episodes, BRT:293-384): select + env step only, the
+     * table is not updated (pass explore thresholds of 0 for the reference's deterministic=True, exploration_rate=0) */
+    int32_t evaluate;
 } qe_run_t;
 
 int qe_fused_steps(qe_engine_t* e, const qe_agents_t* agents, const qe_run_t* run, void* stream);
