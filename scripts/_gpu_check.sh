@@ -1,2 +1,3 @@
 export PYTHONPATH=$PWD
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+free -g | head -2
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -x -q 2>&1 | tail -15

@@ -1,0 +1,152 @@
+"""Parity at BASELINE.json's full sizes.
+
+Config 3 (1M states x 16 actions, 2^20 agents) is small enough for the C oracle: bit-exact table, states and
+returns after 12 vector steps (well into the clustered regime: half of the agents share a row with more than four
+others).  Config 4's table (100M x 8, 2^22 agents) is checked on one GPU against the oracle on the visited rows,
+plus the size-independent properties of the fused loop: chunking (K steps in one launch == K launches of one
+step) and run-to-run determinism."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle as co  # noqa: E402
+from oracle import rng as orng  # noqa: E402
+from oracle.envs import T_INIT  # noqa: E402
+
+EPS, LR, GAMMA, P_TERM = 0.1, 0.1, 0.99, 0.05
+TT = int(math.ceil(P_TERM * 2.0**32))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu test selected but no CUDA device is visible")
+    from dist_classicrl_b200 import capi as m
+
+    m.lib()
+    return m
+
+
+class Run:
+    """One engine + hash-MDP agents driven through qe_fused_steps."""
+
+    def __init__(self, capi, S, A, N, seed, table_seed):
+        self.capi, self.lib, self.S, self.A, self.N, self.seed = capi, capi.lib(), S, A, N, seed
+        self.h = C.c_void_p()
+        capi.check(self.lib.qe_create(S, A, GAMMA, 0, C.byref(self.h)))
+        capi.check(self.lib.qe_table_fill_random(self.h, table_seed, None))
+        dev = torch.device("cuda:0")
+        self.states = torch.empty(N, dtype=torch.int32, device=dev)
+        self.scratch = torch.empty_like(self.states)
+        self.ep = torch.zeros(N, dtype=torch.float32, device=dev)
+        capi.check(self.lib.qe_mdp_reset(self.states.data_ptr(), None, S, A, seed, None, 4, seed, T_INIT, 0, N, None))
+        self.ag = capi.QeAgents(capi.QE_ENV_MDP, N, self.states.data_ptr(), self.scratch.data_ptr(), None, self.ep.data_ptr(), seed, 0, TT)
+        self.t = 0
+
+    def steps(self, k):
+        th = np.full(k, orng.explore_threshold(EPS), dtype=np.uint64)
+        lr = np.full(k, LR, dtype=np.float32)
+        run = self.capi.QeRun()
+        run.steps = k
+        run.explore_thresholds_host, run.learning_rates_host = th.ctypes.data_as(C.c_void_p), lr.ctypes.data_as(C.c_void_p)
+        run.slots = 4
+        run.stream_seed = run.env_stream_seed = self.seed
+        run.t0 = run.env_t0 = self.t
+        run.use_masks, run.empty_all = 1, int(self.A > 10)
+        self.capi.check(self.lib.qe_fused_steps(self.h, C.byref(self.ag), C.byref(run), None))
+        self.capi.check(self.lib.qe_sync(self.h, None))
+        self.t += k
+
+    def rows(self, states):
+        states = np.ascontiguousarray(states, dtype=np.int32)
+        out = np.empty((states.shape[0], self.A), dtype=np.float32)
+        self.capi.check(self.lib.qe_gather_rows_host(self.h, states.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), states.shape[0]))
+        return out
+
+    def table(self):
+        q = np.empty((self.S, self.A), dtype=np.float32)
+        self.capi.check(self.lib.qe_table_download_host(self.h, q.ctypes.data_as(C.c_void_p)))
+        return q
+
+    def close(self):
+        self.lib.qe_destroy(self.h)
+
+
+def _random_table(S, A, table_seed):
+    x = (np.arange(S * A, dtype=np.uint64) ^ np.uint64((table_seed * 0x9E3779B9) & 0xFFFFFFFF)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(13)
+    x = (x * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    return ((x >> np.uint64(8)).astype(np.float32) * np.float32(2.0**-24)).reshape(S, A)
+
+
+def _oracle(S, A, N, steps, seed, table_seed):
+    st, mk = co.mdp_reset(orng.draw_uniforms(seed, T_INIT, 1, N, 4)[0], S, A, seed)
+    q = _random_table(S, A, table_seed)
+    rew = np.zeros(N, dtype=np.float32)
+    visited = [st.copy()]
+    th = np.full(1, orng.explore_threshold(EPS), dtype=np.uint64)
+    lr = np.full(1, LR, dtype=np.float32)
+    for t in range(steps):
+        res = co.run(co.ENV_MDP, q, None, st, mk, num_states=S, env_seed=seed, term_thresh=TT, uniforms=None, slots=4, stream_seed=seed,
+                     t0=t, steps=1, eps_thresh=th, lr=lr, gamma=GAMMA, empty_all=A > 10, agent_rewards=rew)
+        assert res["rc"] == 0
+        visited.append(st.copy())
+    return q, st, rew, np.unique(np.concatenate(visited))
+
+
+def test_config3_full_size_bit_exact_vs_oracle(capi):
+    S, A, N, steps, seed = 1_000_000, 16, 1 << 20, 12, 0
+    q_o, st_o, rew_o, _ = _oracle(S, A, N, steps, seed, 1)
+    cnt = np.bincount(st_o, minlength=S)
+    assert np.mean(cnt[st_o] > 4) > 0.3, "the run must reach the clustered regime"
+    r = Run(capi, S, A, N, seed, 1)
+    try:
+        r.steps(5)
+        r.steps(7)
+        assert np.array_equal(r.states.cpu().numpy(), st_o)
+        assert np.array_equal(r.ep.cpu().numpy(), rew_o)
+        assert np.array_equal(r.table(), q_o)
+    finally:
+        r.close()
+
+
+def test_config4_table_size_visited_rows_vs_oracle(capi):
+    S, A, N, steps, seed = 100_000_000, 8, 1 << 22, 3, 0
+    q_o, st_o, rew_o, visited = _oracle(S, A, N, steps, seed, 1)
+    r = Run(capi, S, A, N, seed, 1)
+    try:
+        r.steps(steps)
+        assert np.array_equal(r.states.cpu().numpy(), st_o)
+        assert np.array_equal(r.ep.cpu().numpy(), rew_o)
+        assert np.array_equal(r.rows(visited), q_o[visited])  # every row any agent ever stood on
+        probe = np.arange(0, S, 9973, dtype=np.int32)          # and a stride of untouched ones
+        assert np.array_equal(r.rows(probe), q_o[probe])
+    finally:
+        r.close()
+
+
+def test_config3_chunking_and_determinism(capi):
+    S, A, N, seed = 1_000_000, 16, 1 << 20, 3
+    a, b, c = (Run(capi, S, A, N, seed, 1) for _ in range(3))
+    try:
+        a.steps(8)
+        for _ in range(8):
+            b.steps(1)
+        c.steps(3)
+        c.steps(5)
+        sa, ea, qa = a.states.cpu().numpy(), a.ep.cpu().numpy(), a.table()
+        for other in (b, c):
+            assert np.array_equal(other.states.cpu().numpy(), sa)
+            assert np.array_equal(other.ep.cpu().numpy(), ea)
+            assert np.array_equal(other.table(), qa)
+    finally:
+        for x in (a, b, c):
+            x.close()
