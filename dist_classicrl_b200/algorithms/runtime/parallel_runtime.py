@@ -53,7 +53,7 @@ class ParallelQLearning(BaseRuntime):
             for e, slot in zip(envs, slots):
                 if self._can_fuse(e):
                     slot["episode_rewards"].extend(self._run_fused(e, block, slot["rewards"]))
-                    slot["states"] = e._obs()
+                    slot["states"] = e._obs_lazy()
                 else:
                     for _ in range(block):
                         slot["states"], slot["infos"] = self.run_single_step(e, slot["states"], slot["rewards"],

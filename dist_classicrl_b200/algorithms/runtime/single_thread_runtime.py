@@ -33,7 +33,7 @@ class SingleThreadQLearning(BaseRuntime):
             states, infos, agent_rewards = curr_state_dict["states"], curr_state_dict["infos"], curr_state_dict["rewards"]
         if self._can_fuse(env):
             reward_history = self._run_fused(env, steps, agent_rewards, trace=trace)
-            states = env._obs()
+            states = env._obs_lazy()
             if self.history_mode == "full":
                 mean = sum(reward_history) / len(reward_history)  # ZeroDivisionError if no episode ended (STR:67)
             else:

@@ -159,8 +159,8 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     e->T.q = e->q_real;
     CK(cudaMalloc(&e->T.err, sizeof(int)));
     CK(cudaMemset(e->T.err, 0, sizeof(int)));
-    CK(cudaMalloc(&e->tile_counter, 4 * sizeof(int)));
-    CK(cudaMemset(e->tile_counter, 0, 4 * sizeof(int)));
+    CK(cudaMalloc(&e->tile_counter, 8 * sizeof(int)));
+    CK(cudaMemset(e->tile_counter, 0, 8 * sizeof(int)));
     CK(cudaMalloc(&e->phase_ns, 33 * sizeof(uint64_t)));
     CK(cudaMemset(e->phase_ns, 0, 33 * sizeof(uint64_t)));
     int rc = ensure_agents(e, 1024);
@@ -303,7 +303,7 @@ static int launch_learn_exact(qe_engine* e, const int32_t* s, const int32_t* a, 
     Table T = e->T;
     float gamma = e->gamma;
     int* cursor = e->tile_counter;
-    CK(cudaMemsetAsync(cursor, 0, 4 * sizeof(int), st));
+    CK(cudaMemsetAsync(cursor, 0, 8 * sizeof(int), st));
     void* args[] = {&T, &s, &a, &r, &s2, &term, &m2, &lr, &gamma, &epoch, &cursor, &n};
     CK(cudaLaunchCooperativeKernel((void*)learn_exact_kernel<LPR>, dim3(blocks), dim3(256), args, 0, st));
     e->launches++;
@@ -591,7 +591,7 @@ int qe_fused_steps(qe_engine_t* e, const qe_agents_t* ag, const qe_run_t* run, v
     F.empty_all = run->empty_all; F.use_masks = run->use_masks; F.gamma = e->gamma;
     F.step0 = e->step;
     F.tile_counter = e->tile_counter;
-    CK(cudaMemsetAsync(e->tile_counter, 0, 4 * sizeof(int), st));
+    CK(cudaMemsetAsync(e->tile_counter, 0, 8 * sizeof(int), st));
     F.trace_actions = run->trace_actions; F.trace_rewards = run->trace_rewards; F.trace_term = run->trace_terminated;
     F.trace_next = run->trace_next_states; F.trace_epret = run->trace_episode_returns;
     F.ep_sum = run->episode_sum; F.ep_count = run->episode_count;

@@ -282,7 +282,7 @@ __device__ __forceinline__ int pick_action(int num_actions, uint32_t valid, uint
 //   m       max over the legal cells of s'_i whose value "just before i" is already known: cells nobody writes
 //           (table) and cells written only by agents >= i (Q0 as captured by one of them in tr_p)
 //   d0..d3  earlier writers of the remaining legal cells (latest one per cell) whose published value is needed, or -1
-//   dyn     crowded bootstrap row (> 4 writers): contested actions; their writers sit in the shared-memory table best[]
+//   dyn     crowded bootstrap row (> 4 writers): actions with an earlier writer; the writers sit in the shared-memory table best[]
 struct Scan {
     float m;
     int pj, d0, d1, d2, d3;
@@ -345,7 +345,10 @@ __device__ __forceinline__ Scan scan_writers(const Table& T, int* best, bool act
     float m_fix = -INFINITY;
     sc.d0 = sc.d1 = sc.d2 = sc.d3 = -1;
     if (boot && mask2 == 0u) atomicOr(T.err, kErrEmpty);  // np.max of an empty selection (QLO:764)
-    if (c2 <= 4u) {
+#ifndef QE_FAST_WRITERS
+#define QE_FAST_WRITERS 4u  // rows with at most this many writers take the branch-free path (0: always the general walk)
+#endif
+    if (c2 <= QE_FAST_WRITERS) {
         uint32_t ak[4], lk[4], beaten[4];
         int jk[4], key[4];
 #pragma unroll
@@ -384,30 +387,34 @@ __device__ __forceinline__ Scan scan_writers(const Table& T, int* best, bool act
         w2.e = make_uint4(I2.w[4], I2.w[5], I2.w[6], I2.w[7]);
         w2.count = c2;
         w2.ovf = (I2.w[3] == epoch) ? (I2.w[2] & kNone) : kNone;
-        for (uint32_t b = mask2; b; b &= b - 1u) best[(__ffs(b) - 1) * 256] = -1;
+        // best[a] = latest earlier writer of (s', a) if bit a of `early` is set, else (bit a of `late`) some later writer
+        uint32_t early = 0u, late = 0u;
         for_each_writer(T, w2, [&](uint32_t w) {
-            const uint32_t aj = w >> 24;
-            if ((mask2 >> aj) & 1u) {
-                contested |= 1u << aj;
+            const uint32_t aj = (w >> 24) & 31u, bit = 1u << aj;
+            if (mask2 & bit) {
                 const int j = (int)(w & kNone);
                 int* b = best + aj * 256;
-                const int cur = *b;
-                if (j < i) *b = cur >= 0 ? max(cur, j) : j;
-                else if (cur == -1) *b = -(j + 2);
+                if (j < i) {
+                    *b = (early & bit) ? max(*b, j) : j;
+                    early |= bit;
+                } else if (!((early | late) & bit)) {
+                    *b = j;
+                    late |= bit;
+                }
             }
         });
+        contested = early | late;
+        for (uint32_t b = late & ~early; b; b &= b - 1u)  // written only by agents >= i: Q0 as captured by one of them
+            m_fix = fmax_plain(m_fix, __ldcg(T.tr_p + best[(__ffs(b) - 1) * 256]));
         if (SLOW_OK) {
-            sc.dyn = contested;  // resolved from best[] in the polling loop
-        } else {                 // up to four earlier writers fit the deferred record; more -> in-order pass
+            sc.dyn = early;  // resolved from best[] in the polling loop
+        } else {             // up to four earlier writers fit the deferred record; more -> in-order pass
             int nd = 0;
-            for (uint32_t b = contested; b; b &= b - 1u) {
+            for (uint32_t b = early; b; b &= b - 1u) {
                 const int jb = best[(__ffs(b) - 1) * 256];
-                if (jb < 0) m_fix = fmax_plain(m_fix, __ldcg(T.tr_p + (-jb - 2)));
-                else {
-                    if (nd == 0) sc.d0 = jb; else if (nd == 1) sc.d1 = jb; else if (nd == 2) sc.d2 = jb; else if (nd == 3) sc.d3 = jb;
-                    else sc.slow = 1u;
-                    ++nd;
-                }
+                if (nd == 0) sc.d0 = jb; else if (nd == 1) sc.d1 = jb; else if (nd == 2) sc.d2 = jb; else if (nd == 3) sc.d3 = jb;
+                else sc.slow = 1u;
+                ++nd;
             }
         }
     }
@@ -752,14 +759,9 @@ struct InOrderLanes {
                 uint32_t left = 0;
                 for (uint32_t b = dyn; b; b &= b - 1u) {
                     const int a2 = __ffs(b) - 1;
-                    const int jb = best[a2 * 256];
-                    if (jb < 0) {
-                        m = fmax_plain(m, __ldcg(T.tr_p + (-jb - 2)));
-                    } else {
-                        const uint64_t w = ld_relaxed_u64(T.slot + jb);
-                        if ((uint32_t)(w >> 32) == epoch) m = fmax_plain(m, __uint_as_float((uint32_t)w));
-                        else left |= 1u << a2;
-                    }
+                    const uint64_t w = ld_relaxed_u64(T.slot + best[a2 * 256]);
+                    if ((uint32_t)(w >> 32) == epoch) m = fmax_plain(m, __uint_as_float((uint32_t)w));
+                    else left |= 1u << a2;
                 }
                 dyn = left;
             }
@@ -814,14 +816,23 @@ __global__ void __launch_bounds__(256) learn_exact_kernel(Table T, const int32_t
         row_insert(T, i, s, a, __ldcg(T.q + (size_t)s * T.ld + a), epoch);
     }
     grid.sync();
-    for (int base = (tid & ~31); base < n; base += nthreads) {
-        const int i = base + lane;
-        const bool active = i < n;
-        const int ii = active ? i : 0;
-        const uint32_t m2 = next_mask_bits ? (next_mask_bits[ii] & full) : full;
-        const int kind = learn_first_pass<LPR>(T, s_best + threadIdx.x, active, i, states[ii], actions[ii], rewards[ii],
-                                               __ldcg(T.tr_p + ii), next_states[ii], terminated[ii] != 0, m2, lr, gamma, epoch);
-        store_tile_masks(T, base >> 5, kind, cursor + 2);
+    {
+        int* claim = cursor + 4;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(claim, 32);
+        base = __shfl_sync(kFull, base, 0);
+        while (base < n) {
+            int next_base = 0;
+            if (lane == 0) next_base = atomicAdd(claim, 32);
+            const int i = base + lane;
+            const bool active = i < n;
+            const int ii = active ? i : 0;
+            const uint32_t m2 = next_mask_bits ? (next_mask_bits[ii] & full) : full;
+            const int kind = learn_first_pass<LPR>(T, s_best + threadIdx.x, active, i, states[ii], actions[ii], rewards[ii],
+                                                   __ldcg(T.tr_p + ii), next_states[ii], terminated[ii] != 0, m2, lr, gamma, epoch);
+            store_tile_masks(T, base >> 5, kind, cursor + 2);
+            base = __shfl_sync(kFull, next_base, 0);
+        }
     }
     grid.sync();
     second_pass_all<LPR>(T, s_best + threadIdx.x, cursor, __ldcg(cursor + 2) != 0, n, states, next_states,
@@ -1048,7 +1059,7 @@ struct FusedArgs {
     int empty_all, use_masks;
     float gamma;
     uint32_t step0;              // engine-global step counter at launch (epoch source)
-    int* tile_counter;           // [4] in-order cursors [0,1] and crowded-agent counts [2,3] (double-buffered across steps), 0 at launch
+    int* tile_counter;           // [6] in-order cursors [0,1], crowded-agent counts [2,3], first-pass tile claims [4,5] (double-buffered across steps), 0 at launch
     int32_t* trace_actions;
     float* trace_rewards;
     uint8_t* trace_term;
@@ -1182,17 +1193,28 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
         if (F.evaluate) continue;  // the table is read-only: nothing to update, the barrier above orders the state buffers
 
         // ---------------- phase B1: exact sequential TD update, first pass (agents that wait for nobody finish)
-        for (int base = (tid & ~31); base < n; base += nthreads) {
-            const int i = base + lane;
-            const bool active = i < n;
-            const int ii = active ? i : 0;
-            const uint8_t at = F.tr_a[ii];
-            const int s2 = nxt[ii];
-            const uint32_t ew = (ENV == 1) ? F.envw[ii] : 0u;
-            const uint32_t m2 = F.use_masks ? env_mask<ENV>(s2, ew, T.A, F.env_seed) : full;
-            const int kind = learn_first_pass<LPR>(T, s_best + threadIdx.x, active, i, cur[ii], at & 0x7F, F.tr_r[ii],
-                                                   __ldcg(T.tr_p + ii), s2, (at & 0x80) != 0, m2, lr, F.gamma, epoch);
-            store_tile_masks(T, base >> 5, kind, F.tile_counter + 2 + (k & 1));
+        // Tiles are claimed from a counter (crowded tiles cost several times more than sparse ones); the next claim
+        // is issued before the current tile is processed so that its round trip is hidden.
+        {
+            int* claim = F.tile_counter + 4 + (k & 1);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(claim, 32);
+            base = __shfl_sync(kFull, base, 0);
+            while (base < n) {
+                int next_base = 0;
+                if (lane == 0) next_base = atomicAdd(claim, 32);
+                const int i = base + lane;
+                const bool active = i < n;
+                const int ii = active ? i : 0;
+                const uint8_t at = F.tr_a[ii];
+                const int s2 = nxt[ii];
+                const uint32_t ew = (ENV == 1) ? F.envw[ii] : 0u;
+                const uint32_t m2 = F.use_masks ? env_mask<ENV>(s2, ew, T.A, F.env_seed) : full;
+                const int kind = learn_first_pass<LPR>(T, s_best + threadIdx.x, active, i, cur[ii], at & 0x7F, F.tr_r[ii],
+                                                       __ldcg(T.tr_p + ii), s2, (at & 0x80) != 0, m2, lr, F.gamma, epoch);
+                store_tile_masks(T, base >> 5, kind, F.tile_counter + 2 + (k & 1));
+                base = __shfl_sync(kFull, next_base, 0);
+            }
         }
         grid.sync();
         if (clk && k < 10) F.phase_ns[2 + 3 * k] = global_ns();
@@ -1207,6 +1229,7 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
         if (tid == 0) {  // the other cursor / crowded-agent count are idle until the next step
             F.tile_counter[(k + 1) & 1] = 0;
             F.tile_counter[2 + ((k + 1) & 1)] = 0;
+            F.tile_counter[4 + ((k + 1) & 1)] = 0;
         }
         grid.sync();
         if (clk && k < 10) F.phase_ns[3 + 3 * k] = global_ns();

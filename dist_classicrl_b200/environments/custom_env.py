@@ -54,6 +54,51 @@ def _torch():
     return torch
 
 
+class _LazyObs(dict):
+    def __init__(self, env) -> None:
+        super().__init__()
+        self._env = env
+        self._snap = (env.states.clone(), env.mask_bits.clone())  # the observation of THIS moment (cheap: 8 B / agent)
+
+    def _fill(self) -> None:
+        if self._env is not None:
+            env, self._env = self._env, None
+            super().update(env._obs(*self._snap))
+            self._snap = None
+
+    def __getitem__(self, key):
+        self._fill()
+        return super().__getitem__(key)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self) -> int:
+        self._fill()
+        return super().__len__()
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def values(self):
+        self._fill()
+        return super().values()
+
+    def __contains__(self, key) -> bool:
+        self._fill()
+        return super().__contains__(key)
+
+    def get(self, key, default=None):
+        self._fill()
+        return super().get(key, default)
+
+
 class DeviceVecEnv(DistClassicRLEnv):
     """Base of the GPU-resident vector environments (state lives in HBM, one thread per agent steps it).
 
@@ -111,15 +156,22 @@ class DeviceVecEnv(DistClassicRLEnv):
         shifts = torch.arange(self.num_actions, device=self.device, dtype=torch.int32)
         return (bits.unsqueeze(1) >> shifts.unsqueeze(0)) & 1
 
-    def _obs(self):
+    def _obs_lazy(self):
+        """Observation after a fused run: a dict whose entries are built from the device state on first access
+        (a caller that hands it straight back to ``run_steps`` never pays for the ``[N, A]`` mask array)."""
+        return _LazyObs(self) if self.dict_obs else self._obs()
+
+    def _obs(self, states=None, mask_bits=None):
+        states = self.states if states is None else states
+        mask_bits = self.mask_bits if mask_bits is None else mask_bits
         if self.output == "torch":
             if not self.dict_obs:
-                return self.states.clone()
-            return {"observation": self.states.clone(), "action_mask": self._mask_array(self.mask_bits)}
-        st = self.states.cpu().numpy().astype(np.int64)
+                return states.clone()
+            return {"observation": states.clone(), "action_mask": self._mask_array(mask_bits)}
+        st = states.cpu().numpy().astype(np.int64)
         if not self.dict_obs:
             return st
-        return {"observation": st, "action_mask": self._mask_array(self.mask_bits).cpu().numpy().astype(np.int64)}
+        return {"observation": st, "action_mask": self._mask_array(mask_bits).cpu().numpy().astype(np.int64)}
 
     def _actions_dev(self, actions):
         torch = _torch()

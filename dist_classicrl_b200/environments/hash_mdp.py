@@ -53,16 +53,6 @@ class HashMDPVecEnv(DeviceVecEnv):
         return self._finish_step(rewards, term)
 
     def refresh_after_fused(self) -> None:
-        # masks are a pure function of the state: recompute them with a zero-step reset-free kernel call
-        s = self.states.to(_torch().int64)
-        x = (s + ((self.env_seed * 0x632BE5AB) & 0xFFFFFFFF)) & 0xFFFFFFFF
-        x = (x + ((0x9E3779B9 * 3) & 0xFFFFFFFF)) & 0xFFFFFFFF
-        x = x ^ (x >> 16)
-        x = (x * 0x85EBCA6B) & 0xFFFFFFFF
-        x = x ^ (x >> 13)
-        x = (x * 0xC2B2AE35) & 0xFFFFFFFF
-        x = x ^ (x >> 16)
-        full = (1 << self.num_actions) - 1
-        bits = (x & full) | 1
-        bits = _torch().where(bits >= 2**31, bits - 2**32, bits)
-        self.mask_bits = bits.to(_torch().int32)
+        # masks are a pure function of the state
+        capi.check(self._lib.qe_mdp_masks(self.states.data_ptr(), self.mask_bits.data_ptr(), self.num_actions, self.env_seed,
+                                          self.num_envs, self._stream()))
