@@ -1,6 +1,4 @@
 export PYTHONPATH=$PWD
-timeout 120 python scripts/dense_probe.py 100000 16 100000 10
-timeout 120 python scripts/dense_probe.py 100000 16 100000 10
-timeout 60 python scripts/perf_probe.py 1e5 16 100000 10 4 | tail -8
-timeout 60 python scripts/perf_probe.py 1e8 8 4194304 10 2 2>&1 | tail -5
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 600 python bench.py > gpurun_out/bench_r1_c.json 2> gpurun_out/bench_r1_c.err; echo "bench rc $?"; tail -3 gpurun_out/bench_r1_c.err; cat gpurun_out/bench_r1_c.json
+timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_r1_ref.json 2>&1; cat gpurun_out/bench_r1_ref.json

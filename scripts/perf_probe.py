@@ -1,5 +1,6 @@
 """Quick device-only timing of the fused loop at the C-ABI level (development aid)."""
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -32,6 +33,7 @@ def launch(t0, stats=True):
     run.slots = 4
     run.t0 = run.env_t0 = t0
     run.use_masks = 1
+    run.evaluate = int(os.environ.get('QE_EVAL', '0'))
     run.empty_all = int(A > 10)
     if stats:
         run.episode_sum, run.episode_count = es.data_ptr(), ec.data_ptr()
