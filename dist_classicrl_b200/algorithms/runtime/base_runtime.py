@@ -193,6 +193,36 @@ class BaseRuntime(ABC):
             return False
         return algo.action_size <= 32 and env.num_actions == algo.action_size and env.num_states == algo.state_size
 
+    def _uniforms_on_device(self, rng, block, t0: int, k: int, n: int, dev):
+        """Device copy of the pre-drawn uniforms ``[t0, t0+k)``.  The block after it is copied on a side stream right
+        away (asynchronously when the host array is pinned), so the next call's host-to-device copy overlaps this
+        call's kernel."""
+        import torch
+
+        main = torch.cuda.current_stream()
+        cached = getattr(rng, "_prefetched", None)
+        if cached is not None and cached[0] == (t0, k, n, str(dev)):
+            main.wait_event(cached[2])
+            u_dev = cached[1]
+        else:
+            u_dev = torch.from_numpy(block.view(np.int32)).to(dev)
+        rng._prefetched = None
+        nxt = rng.uniforms[t0 + k:t0 + 2 * k, :n]
+        if nxt.shape[0] == k and nxt.flags.c_contiguous:
+            src = torch.from_numpy(nxt.view(np.int32))
+            if src.is_pinned():
+                side = getattr(self, "_copy_stream", None)
+                if side is None:
+                    side = self._copy_stream = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(side):
+                    ahead = torch.empty(src.shape, dtype=torch.int32, device=dev)
+                    ahead.copy_(src, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                ahead.record_stream(main)
+                rng._prefetched = ((t0 + k, k, n, str(dev)), ahead, done)
+        return u_dev
+
     def _run_fused(self, env, steps: int, agent_rewards, *, trace: dict | None = None, evaluate: bool = False,
                    history_rows: bool = False) -> list[float]:
         """K vector steps in ``qe_fused_steps`` launches; returns the episode-reward history (agent order
@@ -239,7 +269,7 @@ class BaseRuntime(ABC):
                 block = np.ascontiguousarray(algo._rng.uniforms[t0:t0 + k, :n])
                 if block.shape[0] < k:
                     raise IndexError("pre-drawn uniform stream exhausted")
-                u_dev = torch.from_numpy(block.view(np.int32)).to(dev)
+                u_dev = self._uniforms_on_device(algo._rng, block, t0, k, n, dev)
                 run.uniforms = u_dev.data_ptr()
                 run.slots = block.shape[2]
                 algo._rng.t += k

@@ -143,7 +143,7 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
         const int ld = 4 * info_off;
         e->ld = ld;
         e->T.info_off = info_off;
-        e->T.inline_cap = ld - info_off - 4;
+        e->T.inline_cap = ld - info_off - 4 - 2;  // two words behind the inline entries hold the spill descriptor
     } else {  // generic path (sequential learn kernel): plain padded rows, no writer info
         e->ld = ((num_actions + 3) / 4) * 4;
         e->T.info_off = 0;
@@ -161,6 +161,10 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     CK(cudaMemset(e->T.err, 0, sizeof(int)));
     CK(cudaMalloc(&e->tile_counter, 8 * sizeof(int)));
     CK(cudaMemset(e->tile_counter, 0, 8 * sizeof(int)));
+    e->T.spill_slots = 1024;
+    CK(cudaMalloc(&e->T.spill, sizeof(uint32_t) * (size_t)e->T.spill_slots * kSpillCap));
+    CK(cudaMalloc(&e->T.spill_next, 2 * sizeof(int)));
+    CK(cudaMemset(e->T.spill_next, 0, 2 * sizeof(int)));
     CK(cudaMalloc(&e->phase_ns, 33 * sizeof(uint64_t)));
     CK(cudaMemset(e->phase_ns, 0, 33 * sizeof(uint64_t)));
     int rc = ensure_agents(e, 1024);
@@ -173,7 +177,7 @@ int qe_destroy(qe_engine_t* e) {
     if (!e) return QE_OK;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    cudaFree(e->q_real); cudaFree(e->T.later_buf); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
+    cudaFree(e->q_real); cudaFree(e->T.later_buf); cudaFree(e->T.spill); cudaFree(e->T.spill_next); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
     delete e;
     return QE_OK;
@@ -304,6 +308,7 @@ static int launch_learn_exact(qe_engine* e, const int32_t* s, const int32_t* a, 
     float gamma = e->gamma;
     int* cursor = e->tile_counter;
     CK(cudaMemsetAsync(cursor, 0, 8 * sizeof(int), st));
+    CK(cudaMemsetAsync(e->T.spill_next, 0, 2 * sizeof(int), st));
     void* args[] = {&T, &s, &a, &r, &s2, &term, &m2, &lr, &gamma, &epoch, &cursor, &n};
     CK(cudaLaunchCooperativeKernel((void*)learn_exact_kernel<LPR>, dim3(blocks), dim3(256), args, 0, st));
     e->launches++;
@@ -592,6 +597,7 @@ int qe_fused_steps(qe_engine_t* e, const qe_agents_t* ag, const qe_run_t* run, v
     F.step0 = e->step;
     F.tile_counter = e->tile_counter;
     CK(cudaMemsetAsync(e->tile_counter, 0, 8 * sizeof(int), st));
+    CK(cudaMemsetAsync(e->T.spill_next, 0, 2 * sizeof(int), st));
     F.trace_actions = run->trace_actions; F.trace_rewards = run->trace_rewards; F.trace_term = run->trace_terminated;
     F.trace_next = run->trace_next_states; F.trace_epret = run->trace_episode_returns;
     F.ep_sum = run->episode_sum; F.ep_count = run->episode_count;

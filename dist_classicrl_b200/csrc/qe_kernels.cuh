@@ -34,6 +34,8 @@ namespace qe {
 namespace cg = cooperative_groups;
 
 constexpr uint32_t kNone = 0xFFFFFFu;       // list terminator (24-bit agent index)
+constexpr uint32_t kSpillCap = 4096;        // entries per spill array
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kErrInvalidMove = 1, kErrEmpty = 2, kErrTimeout = 4;
 constexpr uint64_t kTimeoutNs = 4000000000ull;  // a TD update that has not drained after 4 s is reported, not waited for
@@ -43,7 +45,10 @@ struct Table {
     int ld;            // floats per row block (power of two)
     int A;             // actions
     int info_off;      // float offset of the writer info inside a row block
-    int inline_cap;    // writer entries stored inline in the row block (>= 4)
+    int inline_cap;    // writer entries stored inline in the row block (>= 4); the two words after them hold the spill descriptor
+    uint32_t* spill;   // [spill_slots][kSpillCap] contiguous writer entries of crowded rows (beyond the inline ones)
+    int spill_slots;
+    int* spill_next;   // [2] slots handed out in this step (by epoch parity; the other one is reset meanwhile)
     uint32_t* node;    // [cap] overflow list: (action << 24) | next24
     uint64_t* slot;    // [cap] (epoch << 32) | float bits of v_i
     float* tr_p;       // [cap] Q0[s_i, a_i] captured before any commit of this step
@@ -67,18 +72,45 @@ __device__ __forceinline__ uint64_t global_ns() {
 }
 
 // ------------------------------------------------------------------ phase 1: register agent i as a writer of row s
+// Entry `ticket` of a row's writer list.  The first inline_cap entries live in the row block.  The agent that draws
+// ticket == inline_cap claims a spill array for the row and publishes {slot, epoch} in the descriptor behind the inline
+// entries; later arrivals wait for the descriptor (its writer is resident and waits for nobody) and store at
+// spill[slot][ticket - inline_cap] -- crowded rows stay contiguous and are read with whole-sector loads.  Only what
+// does not fit there (no slot left, or more than kSpillCap entries) goes to the per-agent linked list.
+__device__ __forceinline__ void list_insert(const Table& T, unsigned long long* info, int i, int a, uint32_t epoch) {
+    const unsigned long long old = atomicExch(info + 1, ((unsigned long long)epoch << 32) | (unsigned long long)i);
+    T.node[i] = ((uint32_t)a << 24) | (((uint32_t)(old >> 32) == epoch) ? ((uint32_t)old & kNone) : kNone);
+}
+__device__ __forceinline__ void store_entry(const Table& T, unsigned long long* info, uint32_t ticket, int i, int a, uint32_t epoch) {
+    uint32_t* words = reinterpret_cast<uint32_t*>(info);
+    const uint32_t entry = (uint32_t)i | ((uint32_t)a << 24);
+    const uint32_t cap = (uint32_t)T.inline_cap;
+    if (ticket < cap) {
+        words[4 + ticket] = entry;
+        return;
+    }
+    uint64_t* desc = reinterpret_cast<uint64_t*>(words + 4 + cap);
+    uint32_t slot = kNoSlot;
+    if (ticket == cap) {  // the claiming lane publishes before any lane of its own warp starts to wait (next statement)
+        const int got = atomicAdd(T.spill_next + (epoch & 1u), 1);
+        slot = got < T.spill_slots ? (uint32_t)got : kNoSlot;
+        st_relaxed_u64(desc, ((uint64_t)epoch << 32) | slot);
+    }
+    if (ticket > cap) {
+        uint64_t d;
+        do { d = ld_relaxed_u64(desc); } while ((uint32_t)(d >> 32) != epoch);
+        slot = (uint32_t)d;
+    }
+    const uint32_t idx = ticket - cap;
+    if (slot != kNoSlot && idx < kSpillCap) T.spill[(size_t)slot * kSpillCap + idx] = entry;
+    else list_insert(T, info, i, a, epoch);
+}
 __device__ __forceinline__ void row_insert(const Table& T, int i, int s, int a, float p, uint32_t epoch) {
     T.tr_p[i] = p;
     unsigned long long* info = reinterpret_cast<unsigned long long*>(row_info(T, s));
-    const unsigned long long base = (unsigned long long)epoch << 32;
-    atomicMax(info, base);  // a stale (older-epoch) counter restarts at {epoch, 0}
+    atomicMax(info, (unsigned long long)epoch << 32);  // a stale (older-epoch) counter restarts at {epoch, 0}
     const uint32_t c = (uint32_t)atomicAdd(info, 1ull);
-    if (c < (uint32_t)T.inline_cap) {
-        reinterpret_cast<uint32_t*>(info)[4 + c] = (uint32_t)i | ((uint32_t)a << 24);
-    } else {
-        const unsigned long long old = atomicExch(info + 1, base | (unsigned long long)i);
-        T.node[i] = ((uint32_t)a << 24) | (((uint32_t)(old >> 32) == epoch) ? ((uint32_t)old & kNone) : kNone);
-    }
+    store_entry(T, info, c, i, a, epoch);
 }
 
 struct RowWriters {  // snapshot of a row's writer info (taken after the grid barrier)
@@ -112,11 +144,33 @@ __device__ __forceinline__ void for_each_writer_from4(const Table& T, const RowW
                 if (base + t < ninl) f(e[t]);
         }
         if (w.count > (uint32_t)T.inline_cap) {
-            uint32_t j = w.ovf;
-            while (j != kNone) {
-                const uint32_t nd = __ldcg(T.node + j);
-                f(j | (nd & 0xFF000000u));
-                j = nd & kNone;
+            // spill array (whole sectors, two in flight), then whatever had to go to the linked list
+            const uint64_t d = ld_relaxed_u64(reinterpret_cast<const uint64_t*>(w.iw + 4 + T.inline_cap));
+            const uint32_t slot = (uint32_t)d;
+            uint32_t nsp = 0;
+            if (slot != kNoSlot) {
+                nsp = min(w.count - (uint32_t)T.inline_cap, kSpillCap);
+                const uint32_t* sp = T.spill + (size_t)slot * kSpillCap;
+                for (uint32_t base = 0; base < nsp; base += 16) {
+                    uint32_t e[16];
+                    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
+                                 : "l"(sp + base));
+                    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(e[8]), "=r"(e[9]), "=r"(e[10]), "=r"(e[11]), "=r"(e[12]), "=r"(e[13]), "=r"(e[14]), "=r"(e[15])
+                                 : "l"(sp + base + 8));
+#pragma unroll
+                    for (int t = 0; t < 16; ++t)
+                        if (base + t < nsp) f(e[t]);
+                }
+            }
+            if (w.count - (uint32_t)T.inline_cap > nsp) {
+                uint32_t j = w.ovf;
+                while (j != kNone) {
+                    const uint32_t nd = __ldcg(T.node + j);
+                    f(j | (nd & 0xFF000000u));
+                    j = nd & kNone;
+                }
             }
         }
     }
@@ -938,16 +992,27 @@ __global__ void serve_bootstrap_kernel(Table T, const int32_t* __restrict__ rows
     const uint32_t legal = masks ? (masks[r] & full) : full;
     RowWriters w = load_writers(T, row, epoch);
     if (!use_versions) w.count = 0;
+    // the Q row, one 32-byte sector per load (at most four: A <= 32)
+    const int sectors = (T.A + 7) >> 3;
     float m = -INFINITY;
-    for (uint32_t b = legal; b; b &= b - 1u) {
-        const int a2 = __ffs(b) - 1;
-        int best = -1;
-        for_each_writer(T, w, [&](uint32_t e) {
-            const int j = (int)(e & kNone);
-            if ((int)(e >> 24) == a2 && j < before) best = max(best, j);
-        });
-        const float v = best >= 0 ? __uint_as_float((uint32_t)ld_relaxed_u64(T.slot + best)) : __ldcg(T.q + (size_t)row * T.ld + a2);
-        m = fmax_plain(m, v);
+    uint32_t versioned = 0u;  // legal actions that some earlier local agent writes
+    if (w.count) {
+        for (uint32_t b = legal; b; b &= b - 1u) {
+            const int a2 = __ffs(b) - 1;
+            int best = -1;
+            for_each_writer(T, w, [&](uint32_t e) {
+                const int j = (int)(e & kNone);
+                if ((int)(e >> 24) == a2 && j < before) best = max(best, j);
+            });
+            if (best >= 0) {
+                versioned |= 1u << a2;
+                m = fmax_plain(m, __uint_as_float((uint32_t)ld_relaxed_u64(T.slot + best)));
+            }
+        }
+    }
+    for (int q = 0; q < sectors; ++q) {
+        const uint32_t my = ((legal & ~versioned) >> (8 * q)) & 0xFFu;
+        if (my) m = fmax_plain(m, max8(ld_row8(T.q + (size_t)row * T.ld + 8 * q), my));
     }
     out[r] = m;
 }
@@ -1148,14 +1213,8 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
                     if (term) ew = 0u;
                     s2 = 0;
                 }
-                // writer entry {agent, action}: inline in the row block, overflow -> list through node[]
-                if (F.evaluate) {
-                } else if (ticket < (uint32_t)T.inline_cap) {
-                    reinterpret_cast<uint32_t*>(info)[4 + ticket] = (uint32_t)i | ((uint32_t)a << 24);
-                } else {
-                    const unsigned long long old = atomicExch(info + 1, ((unsigned long long)epoch << 32) | (unsigned long long)i);
-                    T.node[i] = ((uint32_t)a << 24) | (((uint32_t)(old >> 32) == epoch) ? ((uint32_t)old & kNone) : kNone);
-                }
+                // writer entry {agent, action}: inline in the row block, then the row's spill array, then the overflow list
+                if (!F.evaluate) store_entry(T, info, ticket, i, a, epoch);
                 T.tr_p[i] = p;
                 nxt[i] = s2;
                 if (ENV != 0) F.envw[i] = ew;
@@ -1230,6 +1289,7 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
             F.tile_counter[(k + 1) & 1] = 0;
             F.tile_counter[2 + ((k + 1) & 1)] = 0;
             F.tile_counter[4 + ((k + 1) & 1)] = 0;
+            T.spill_next[epoch & 1u] = 0;  // the next step hands out slots from the other counter, the one after it from this one
         }
         grid.sync();
         if (clk && k < 10) F.phase_ns[3 + 3 * k] = global_ns();

@@ -74,11 +74,19 @@ class Transport:
     def all_to_all_v(self, send: Sequence):  # send[d] -> rank d; returns recv[s] from rank s
         raise NotImplementedError
 
+    def all_to_all_known(self, send: Sequence, in_counts: Sequence[int]):
+        """Like :meth:`all_to_all_v` when the receive counts are already known (no count exchange, no host sync)."""
+        return self.all_to_all_v(send)
+
     def all_reduce_sum_(self, tensor):
         raise NotImplementedError
 
     def all_reduce_max_int(self, value: int) -> int:
         raise NotImplementedError
+
+    def all_reduce_max_flag(self, flag) -> int:
+        """Max over ranks of a one-element integer tensor that already lives on the transport's device."""
+        return self.all_reduce_max_int(int(flag.item()))
 
     def all_gather_rows(self, tensor):  # concatenation over ranks along dim 0 (row counts may differ)
         raise NotImplementedError
@@ -124,6 +132,22 @@ class TorchDistTransport(Transport):
             return outs
         dist.all_to_all_single(recv, flat, [n for n in in_splits], [n for n in out_splits], group=self.group)
         return list(torch.split(recv, in_splits, dim=0))
+
+    def all_to_all_known(self, send, in_counts):
+        torch, dist = _torch(), self._dist
+        if dist.get_backend(self.group) == "gloo":
+            return self.all_to_all_v(send)
+        flat = torch.cat(list(send), dim=0).contiguous()
+        recv = torch.empty((sum(in_counts), flat.shape[1]), dtype=flat.dtype, device=flat.device)
+        dist.all_to_all_single(recv, flat, list(in_counts), [int(x.shape[0]) for x in send], group=self.group)
+        return list(torch.split(recv, list(in_counts), dim=0))
+
+    def all_reduce_max_flag(self, flag) -> int:
+        if self._dist.get_backend(self.group) == "gloo":
+            flag = flag.cpu()
+        flag = flag.clone()
+        self._dist.all_reduce(flag, op=self._dist.ReduceOp.MAX, group=self.group)
+        return int(flag.item())
 
     def all_reduce_sum_(self, tensor):
         self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.group)
@@ -240,11 +264,13 @@ def route(transport: Transport, rows, owner):
     return (torch.cat(recv, dim=0) if recv else rows[:0]), order, in_counts
 
 
-def route_back(transport: Transport, answers, in_counts, order):
+def route_back(transport: Transport, answers, in_counts, order, out_counts=None):
     """Inverse of :func:`route`: ``answers`` (one row per received row, same order) go back to the senders and are
-    put into the senders' original row order."""
+    put into the senders' original row order.  ``out_counts`` (how many rows this rank sent to every owner) saves the
+    count exchange."""
     torch = _torch()
-    back = transport.all_to_all_v(list(torch.split(answers, in_counts, dim=0)))
+    parts = list(torch.split(answers, in_counts, dim=0))
+    back = transport.all_to_all_v(parts) if out_counts is None else transport.all_to_all_known(parts, out_counts)
     flat = torch.cat(back, dim=0)
     out = torch.empty_like(flat)
     out[order] = flat
@@ -293,6 +319,7 @@ class ShardedQLearning:
         self.episode_count, self.episode_sum = 0, 0.0
         self.rounds_last = 0
         self.rounds_total = 0
+        self.profile: dict | None = None  # set to {} to collect per-section wall times (synchronising; diagnostics only)
 
     def __del__(self) -> None:
         h, self._h = getattr(self, "_h", None), None
@@ -347,10 +374,24 @@ class ShardedQLearning:
         self._migrate(gid, state, torch.zeros(cnt, dtype=torch.float32, device=self.dev))
         self.t = 0
 
+    def _mark(self, name: str) -> None:
+        if self.profile is not None:
+            import time
+
+            _torch().cuda.synchronize()
+            now = time.perf_counter()
+            self.profile[name] = self.profile.get(name, 0.0) + (now - self._t_mark)
+            self._t_mark = now
+
     # -- one vector step
     def step(self, eps: float, lr: float) -> None:
         torch, lib, h = _torch(), self._lib, self._h
         st = self._stream()
+        if self.profile is not None:
+            import time
+
+            torch.cuda.synchronize()
+            self._t_mark = time.perf_counter()
         n = int(self.gid.shape[0])
         thresh = explore_threshold(eps)
         gid, s_old = self.gid, self.state
@@ -368,6 +409,7 @@ class ShardedQLearning:
                                        self.term_threshold, None, 4, self.seed, self.t, 0, mask2.data_ptr(), rewards.data_ptr(),
                                        term.data_ptr(), n, st))
             capi.check(lib.qe_set_agent_ids(h, None))
+        self._mark("select+env")
         # episode bookkeeping (BRT:212-221)
         acc = self.ep_ret + rewards
         done = term != 0
@@ -376,12 +418,16 @@ class ShardedQLearning:
             self.episode_sum += float(acc[done].double().sum().item())
         self.ep_ret = torch.where(done, torch.zeros_like(acc), acc)
 
+        self._mark("bookkeeping")
         # ---- TD update, exact in global agent order
         own2 = owner_of(s2, self.state_size, self.world).to(torch.int64)
         remote = (~done) & (own2 != self.rank)
         ridx = torch.nonzero(remote).reshape(-1)
         req_rows = torch.stack([gid[ridx], s2[ridx]], dim=1) if n else torch.empty((0, 2), dtype=torch.int32, device=self.dev)
-        got, order, in_counts = route(self.tp, req_rows, own2[ridx])
+        order, out_counts = bucket_by_owner(own2[ridx], self.world)
+        recv = self.tp.all_to_all_v(list(torch.split(req_rows[order], out_counts, dim=0)))
+        in_counts = [int(x.shape[0]) for x in recv]
+        got = torch.cat(recv, dim=0)
         nreq = int(got.shape[0])
         req_s2 = got[:, 1].contiguous()
         req_pos = torch.searchsorted(gid, got[:, 0].contiguous()).to(torch.int32) if nreq else got[:, 0].contiguous()
@@ -392,9 +438,11 @@ class ShardedQLearning:
             if nreq:
                 capi.check(lib.qe_serve_bootstrap(h, req_s2.data_ptr(), req_pos.data_ptr(), req_mask.data_ptr(), answers.data_ptr(),
                                                   nreq, use_versions, st))
-            return route_back(self.tp, answers.view(torch.int32), in_counts, order).view(torch.float32).reshape(-1)
+            return route_back(self.tp, answers.view(torch.int32), in_counts, order, out_counts).view(torch.float32).reshape(-1)
 
+        self._mark("route requests")
         m_ext = serve(0)  # snapshot values to start from
+        self._mark("serve0")
         term_eff = torch.where(remote, torch.ones_like(term), term)
         s2_safe = torch.where(remote, s_old, s2)  # remote rows are never touched locally
         lr32 = float(np.float32(lr))
@@ -408,10 +456,14 @@ class ShardedQLearning:
                 capi.check(lib.qe_learn(h, s_old.data_ptr(), actions.data_ptr(), r_eff.data_ptr(), s2_safe.data_ptr(), term_eff.data_ptr(),
                                         mask2.data_ptr(), None, lr32, n, capi.QE_LEARN_SEQUENTIAL, st))
             rounds += 1
+            self._mark("learn (hold)")
             m_new = serve(1)
-            changed = int((m_new.view(torch.int32) != m_ext.view(torch.int32)).any().item()) if ridx.numel() else 0
+            self._mark("serve")
+            changed = (m_new.view(torch.int32) != m_ext.view(torch.int32)).any().to(torch.int32).reshape(1)
             m_ext = m_new
-            if self.tp.all_reduce_max_int(changed) == 0:
+            stop = self.tp.all_reduce_max_flag(changed) == 0
+            self._mark("converged?")
+            if stop:
                 break
             if rounds > 4096:
                 raise capi.EngineError("sharded TD update did not reach its fixed point")
@@ -422,8 +474,10 @@ class ShardedQLearning:
         self.rounds_last = rounds
         self.rounds_total += rounds
         self.t = (self.t + 1) & 0xFFFFFFFF
+        self._mark("commit")
         # ---- migration to owner(s')
         self._migrate(gid, s2, self.ep_ret)
+        self._mark("migrate")
 
     def run_steps(self, steps: int, exploration_rate_schedule, lr_schedule) -> None:
         """``steps`` vector steps with the reference's schedule protocol (values read, then ``update(N)``, BRT:245-263)."""

@@ -40,13 +40,16 @@ def launch(t0, stats=True):
     capi.check(lib.qe_fused_steps(h, C.byref(ag), C.byref(run), None))
 
 
-launch(0)
+skip = int(os.environ.get('QE_SKIP', '0'))
+for j in range(0, skip, K):
+    launch(j)
+launch(skip)
 capi.check(lib.qe_sync(h, None))
 best = 1e9
 for r in range(reps):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    launch((r + 1) * K)
+    launch(skip + (r + 1) * K)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
