@@ -4,11 +4,13 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 
 #include "../../include/qe_engine.h"
 #include "qe_kernels.cuh"
+#include "qe_sorted.cuh"
 
 using namespace qe;
 
@@ -48,6 +50,9 @@ struct qe_engine {
     float* d_lr = nullptr;
     int sched_cap = 0;
     uint32_t step = 0;       // global step counter (epoch / tag source)
+    SortedScratch X{};       // scratch of the sorted fused loop (qe_sorted.cuh)
+    int sorted_grid = 0;     // ghist was sized for this many blocks
+    int use_sorted = 1;      // fused loop: 1 = sort-based TD update (QE_SORTED=0 selects the writer-list kernel)
     int64_t launches = 0;
     int last_grid = 0;
     std::mutex mu;
@@ -80,6 +85,23 @@ static int ensure_agents(qe_engine* e, int n) {
     CK(cudaMalloc(&e->tr_r, sizeof(float) * cap));
     CK(cudaMalloc(&e->delta, sizeof(float) * cap));
     CK(cudaMemset(e->T.slot, 0, sizeof(uint64_t) * cap));
+    {
+        SortedScratch& X = e->X;
+        for (int b = 0; b < 2; ++b) { cudaFree(X.key[b]); cudaFree(X.val[b]); }
+        cudaFree(X.rank); cudaFree(X.targ); cudaFree(X.mhist); cudaFree(X.rrec); cudaFree(X.rmask); cudaFree(X.hmask);
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaMalloc(&X.key[b], sizeof(int32_t) * cap));
+            CK(cudaMalloc(&X.val[b], sizeof(int32_t) * cap));
+        }
+        CK(cudaMalloc(&X.rank, sizeof(int32_t) * cap));
+        CK(cudaMalloc(&X.targ, sizeof(uint64_t) * cap));
+        CK(cudaMalloc(&X.mhist, sizeof(uint64_t) * cap));
+        CK(cudaMalloc(&X.rrec, sizeof(uint32_t) * 4 * (size_t)cap));
+        CK(cudaMalloc(&X.rmask, sizeof(uint32_t) * (cap / 32)));
+        CK(cudaMalloc(&X.hmask, sizeof(uint32_t) * (cap / 32)));
+        CK(cudaMemset(X.targ, 0, sizeof(uint64_t) * cap));
+        CK(cudaMemset(X.mhist, 0, sizeof(uint64_t) * cap));
+    }
     e->cap = cap;
     return QE_OK;
 }
@@ -161,6 +183,15 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     CK(cudaMemset(e->T.err, 0, sizeof(int)));
     CK(cudaMalloc(&e->tile_counter, 8 * sizeof(int)));
     CK(cudaMemset(e->tile_counter, 0, 8 * sizeof(int)));
+    if (num_actions <= 32) {
+        CK(cudaMalloc(&e->X.seg, sizeof(uint32_t) * 4 * (size_t)e->S));
+        CK(cudaMemset(e->X.seg, 0, sizeof(uint32_t) * 4 * (size_t)e->S));
+        CK(cudaMalloc(&e->X.rowtot, sizeof(int) * kRadix));
+        int bits = 1;
+        while (bits < 31 && (1ll << bits) < e->S) ++bits;
+        e->X.passes = (bits + kRadixBits - 1) / kRadixBits;
+    }
+    e->use_sorted = getenv("QE_SORTED") ? atoi(getenv("QE_SORTED")) : 1;
     e->T.spill_slots = 1024;
     CK(cudaMalloc(&e->T.spill, sizeof(uint32_t) * (size_t)e->T.spill_slots * kSpillCap));
     CK(cudaMalloc(&e->T.spill_next, 2 * sizeof(int)));
@@ -177,6 +208,9 @@ int qe_destroy(qe_engine_t* e) {
     if (!e) return QE_OK;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
+    for (int b = 0; b < 2; ++b) { cudaFree(e->X.key[b]); cudaFree(e->X.val[b]); }
+    cudaFree(e->X.rank); cudaFree(e->X.targ); cudaFree(e->X.mhist); cudaFree(e->X.rrec); cudaFree(e->X.rmask); cudaFree(e->X.hmask);
+    cudaFree(e->X.seg); cudaFree(e->X.rowtot); cudaFree(e->X.ghist);
     cudaFree(e->q_real); cudaFree(e->T.later_buf); cudaFree(e->T.spill); cudaFree(e->T.spill_next); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
     delete e;
@@ -539,9 +573,25 @@ int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t
 template <int ENV, int LPR>
 static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     int blocks = 0;
+    Table T = e->T;
+    if (e->use_sorted && e->state_base == 0) {
+        int rc = coop_blocks(e, fused_sorted_kernel<ENV, LPR>, (long long)F.n, &blocks);
+        if (rc) return rc;
+        if (blocks > e->sorted_grid) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(e->X.ghist);
+            CK(cudaMalloc(&e->X.ghist, sizeof(int) * kRadix * (size_t)blocks));
+            e->sorted_grid = blocks;
+        }
+        SortedScratch X = e->X;
+        void* args[] = {&T, &F, &X};
+        CK(cudaLaunchCooperativeKernel((void*)fused_sorted_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
+        e->launches++;
+        e->last_grid = blocks;
+        return QE_OK;
+    }
     int rc = coop_blocks(e, fused_kernel<ENV, LPR>, (long long)F.n, &blocks);
     if (rc) return rc;
-    Table T = e->T;
     void* args[] = {&T, &F};
     CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
     e->launches++;

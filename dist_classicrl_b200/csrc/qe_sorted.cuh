@@ -1,0 +1,432 @@
+// qe_sorted.cuh -- the sorted form of the fused loop: the exact sequential TD update as segments of a per-step sort.
+//
+// Why.  The bundled environments are deterministic in (s, a), so a greedy policy herds agents: rows with hundreds of
+// writers appear as the table is learned (C3 after 800 vector steps: half of the agents share a row with more than
+// four others, one row has 3333 writers).  Per-agent scans of per-row writer lists are then quadratic in the crowd and
+// same-cell chains resolve one publish-poll round trip per agent.  Sorting the agents by state every step turns each
+// row's writers into one contiguous segment in agent order:
+//
+//   phase A   select + environment step (one lane per agent; nothing is registered anywhere)
+//   phase S   stable LSD radix sort of (state -> agent) : perm[] (agents by (state, agent)), rank[] (its inverse),
+//             segment bounds per row
+//   phase R   readers, one lane per agent: the bootstrap of agent i from row y = s'_i is the masked row max of y after
+//             all writers of y that precede i.  No earlier writer (binary search in y's segment) -> the table row is
+//             still untouched, take its masked max and deposit the target t_i = r_i + gamma*m at i's sorted position.
+//             Otherwise the reader is deferred: it needs mhist[p], the row max after the writer at sorted position p.
+//   phase Q   sequencers, one lane per row: walk the segment in order, v = Q[s,a] + lr*(t - Q[s,a]) from the deposited
+//             targets, publish the row max after every writer in mhist[], park when a target is missing; deferred
+//             readers poll mhist[] and deposit.  Both run as non-blocking sweeps until everything has drained.
+//
+// A chain of c writers of one cell costs its sequencer c steps from registers / shared memory instead of c round trips
+// through L2, and a reader costs O(log c).  Requires the legal-action mask to be a function of the state (true for the
+// device environments: hash MDP, TicTacToe, bandit); the general per-agent-mask update keeps the writer-list kernels.
+#pragma once
+#include "qe_kernels.cuh"
+
+namespace qe {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+
+struct SortedScratch {
+    int32_t* key[2];      // [cap] ping-pong keys (states)
+    int32_t* val[2];      // [cap] ping-pong values (agent indices)
+    int* ghist;           // [kRadix][grid] digit counts per block, scanned in place
+    int* rowtot;          // [kRadix] digit totals
+    int32_t* rank;        // [cap] sorted position of every agent
+    uint64_t* targ;       // [cap] by sorted position: (epoch << 6 | action) << 32 | target bits
+    uint64_t* mhist;      // [cap] by sorted position: epoch << 32 | masked row max after this writer
+    uint32_t* seg;        // [S][4] per state: {segment start, segment end, epoch of both, sequencer progress}
+    uint32_t* rrec;       // [cap][4] deferred readers: {mhist position, own sorted position, reward bits, action}
+    uint32_t* rmask;      // [cap/32] per agent tile: deferred readers
+    uint32_t* hmask;      // [cap/32] per tile of sorted positions: segment heads whose sequencer has not finished
+    int passes;           // radix passes needed for the state range
+};
+
+__device__ __forceinline__ uint32_t ttt_mask_of_state(int s) {  // empty cells of the board a base-3 state id encodes
+    uint32_t m = 0;
+#pragma unroll
+    for (int c = 8; c >= 0; --c) {
+        if (s % 3 == 0) m |= 1u << c;
+        s /= 3;
+    }
+    return m;
+}
+__device__ __forceinline__ float td_target_s(float r, float m, float gamma) { return __fadd_rn(r, __fmul_rn(gamma, m)); }
+__device__ __forceinline__ float td_from_target_s(float p, float target, float lr) {  // QLO:766-768 after the target
+    return __fadd_rn(p, __fmul_rn(lr, __fsub_rn(target, p)));
+}
+template <int ENV>
+__device__ __forceinline__ uint32_t state_mask(int s, int A, uint32_t env_seed, uint32_t full) {
+    if (ENV == 0) return mdp_mask((uint32_t)s, A, env_seed);
+    if (ENV == 1) return ttt_mask_of_state(s);
+    return full;
+}
+
+// ------------------------------------------------------------------ phase S: stable LSD radix sort, inside the grid
+// Every block owns one contiguous chunk of the input, every warp one contiguous part of the chunk.  Per pass: per-warp
+// digit histograms (shared memory) -> block counts to global; grid barrier; per-digit exclusive scan over the blocks
+// (one warp per digit); grid barrier; every warp walks its part in order, 32 keys at a time: position = digit base +
+// blocks before + warps before + earlier keys of the part + earlier lanes with the same digit (match.any).
+template <int WARPS>
+__device__ __forceinline__ void radix_pass(cg::grid_group& grid, int (*whist)[kRadix], const int32_t* kin, const int32_t* vin,
+                                           int32_t* kout, int32_t* vout, int32_t* rank_out, int n, int shift, int* ghist, int* rowtot,
+                                           bool iota_vals) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = gridDim.x, b = blockIdx.x;
+    const int chunk = ((n + nb - 1) / nb + 31) & ~31;          // per block, multiple of 32
+    const int part = ((chunk / 32 + WARPS - 1) / WARPS) * 32;  // per warp, multiple of 32
+    const int lo = min(b * chunk + warp * part, n), hi = min(min(b * chunk + (warp + 1) * part, (b + 1) * chunk), n);
+    for (int d = lane; d < kRadix; d += 32) whist[warp][d] = 0;
+    __syncwarp();
+    for (int base = lo; base < hi; base += 32) {
+        const int x = base + lane;
+        if (x < hi) atomicAdd(&whist[warp][((uint32_t)kin[x] >> shift) & (kRadix - 1)], 1);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) t += whist[w][d];
+        ghist[d * nb + b] = t;
+    }
+    grid.sync();
+    {   // exclusive scan of every digit's row of block counts; one warp per digit
+        const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+        for (int d = gw; d < kRadix; d += nw) {
+            int carry = 0;
+            for (int base = 0; base < nb; base += 32) {
+                const int x = base + lane;
+                const int v = x < nb ? ghist[d * nb + x] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (x < nb) ghist[d * nb + x] = carry + incl - v;
+                carry += __shfl_sync(kFull, incl, 31);
+            }
+            if (lane == 0) rowtot[d] = carry;
+        }
+    }
+    grid.sync();
+    // digit bases (every block redoes the 256-entry scan), then this warp's first free position per digit
+    __shared__ int s_base[kRadix];
+    if (threadIdx.x < 32) {
+        int carry = 0;
+        for (int base = 0; base < kRadix; base += 32) {
+            const int v = rowtot[base + lane];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += y;
+            }
+            s_base[base + lane] = carry + incl - v;
+            carry += __shfl_sync(kFull, incl, 31);
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+        int run = s_base[d] + ghist[d * nb + b];
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const int c = whist[w][d];
+            whist[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int base = lo; base < hi; base += 32) {
+        const int x = base + lane;
+        const bool act = x < hi;
+        const int32_t k = act ? kin[x] : 0;
+        const uint32_t d = act ? (((uint32_t)k >> shift) & (kRadix - 1)) : (uint32_t)kRadix + lane;  // idle lanes match nobody
+        const uint32_t peers = __match_any_sync(kFull, d);
+        if (act) {
+            const int pos = whist[warp][d] + __popc(peers & ((1u << lane) - 1u));
+            const int32_t v = iota_vals ? x : vin[x];
+            kout[pos] = k;
+            vout[pos] = v;
+            if (rank_out) rank_out[v] = pos;
+        }
+        __syncwarp();
+        if (act && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+    grid.sync();
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int ENV, int LPR>
+__global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs F, SortedScratch X) {
+    cg::grid_group grid = cg::this_grid();
+    constexpr int WARPS = 8;
+    __shared__ double s_sum[8];
+    __shared__ unsigned int s_cnt[8];
+    __shared__ int s_whist[WARPS][kRadix];       // radix sort
+    __shared__ float s_vals[8 * LPR * 256];      // sequencers: the row being walked, one column per thread
+    const int lane = threadIdx.x & 31;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    const uint32_t full = T.A >= 32 ? 0xFFFFFFFFu : ((1u << T.A) - 1u);
+    const int n = F.n;
+    const int ntiles = (n + 31) >> 5;
+    const int gwarp = tid >> 5, nwarps = nthreads >> 5;
+    const bool clk = F.phase_ns != nullptr && tid == 0;
+    float* vals = s_vals + threadIdx.x;
+    if (clk) F.phase_ns[0] = global_ns();
+
+    for (int k = 0; k < F.steps; ++k) {
+        const uint32_t epoch = F.step0 + (uint32_t)k + 1u;
+        const uint32_t etag = epoch & 0x3FFFFFFu;  // 26 bits travel with the action in targ[]
+        int32_t* cur = (k & 1) ? F.st_b : F.st_a;
+        int32_t* nxt = (k & 1) ? F.st_a : F.st_b;
+        Uniforms U{F.uniforms ? F.uniforms + (size_t)k * n * F.slots : nullptr, F.slots, F.stream_seed, F.t0 + (uint32_t)k, F.agent0,
+                   F.env_stream_seed, F.env_t0 + (uint32_t)k};
+        const uint64_t thresh = F.eps_thresh[k];
+        const float lr = F.lr[k];
+        double loc_sum = 0.0;
+        unsigned int loc_cnt = 0;
+
+        // ---------------- phase A: select + environment step
+        for (int base = (tid & ~31); base < n; base += nthreads) {
+            const int i = base + lane;
+            const bool active = i < n;
+            int s = 0;
+            uint32_t ew = 0u, valid = 0u, bits1 = 0u;
+            bool explore = false;
+            if (active) {
+                s = cur[i];
+                if (ENV != 0) ew = F.envw[i];
+                valid = F.use_masks ? env_mask<ENV>(s, ew, T.A, F.env_seed) : full;
+                explore = (uint64_t)U.draw(i, 0) < thresh;
+                bits1 = U.draw(i, 1);
+            }
+            RowGather<LPR> rows;
+            rows.issue(T, s, active);
+            float mx;
+            uint32_t tie;
+            rows.row_max_tie(valid, mx, tie);
+            int a = pick_action(T.A, valid, tie, explore, F.empty_all != 0, bits1);
+            if (active && a < 0) { atomicOr(T.err, kErrEmpty); a = 0; }
+            a = max(a, 0);
+            if (active) {
+                int32_t s2 = s;
+                float r = 0.0f;
+                bool term = false;
+                if (ENV == 0) mdp_step(s2, a, (uint32_t)F.S, T.A, F.env_seed, F.term_thresh, U.draw(i, 2), U.draw(i, 3), r, term);
+                else if (ENV == 1) {
+                    if (!ttt_step(ew, a, U.draw(i, 2), U.draw(i, 3), U.draw(i, 4), r, term)) atomicOr(T.err, kErrInvalidMove);
+                    s2 = ttt_state(ew & 0x3FFFFu);
+                } else {
+                    r = (float)a;
+                    ew += 1u;
+                    term = ew >= F.episode_len;
+                    if (term) ew = 0u;
+                    s2 = 0;
+                }
+                nxt[i] = s2;
+                if (ENV != 0) F.envw[i] = ew;
+                F.tr_a[i] = (uint8_t)(a | (term ? 0x80 : 0));
+                F.tr_r[i] = r;
+                float acc = F.ep_ret[i] + r;
+                float fin = __int_as_float(0x7FC00000);
+                if (term) { fin = acc; loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
+                F.ep_ret[i] = acc;
+                const size_t o = (size_t)k * n + i;
+                if (F.trace_actions) F.trace_actions[o] = a;
+                if (F.trace_rewards) F.trace_rewards[o] = r;
+                if (F.trace_term) F.trace_term[o] = term;
+                if (F.trace_next) F.trace_next[o] = s2;
+                if (F.trace_epret) F.trace_epret[o] = fin;
+            }
+            __syncwarp();
+        }
+        if (F.ep_count) {
+            for (int d = 16; d > 0; d >>= 1) {
+                loc_sum += __shfl_xor_sync(kFull, loc_sum, d);
+                loc_cnt += __shfl_xor_sync(kFull, loc_cnt, d);
+            }
+            if (lane == 0) { s_sum[threadIdx.x >> 5] = loc_sum; s_cnt[threadIdx.x >> 5] = loc_cnt; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double bs = 0.0;
+                unsigned int bc = 0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { bs += s_sum[w]; bc += s_cnt[w]; }
+                if (bc) { atomicAdd(F.ep_sum, bs); atomicAdd(F.ep_count, (unsigned long long)bc); }
+            }
+            __syncthreads();
+        }
+        if (F.evaluate) {
+            grid.sync();
+            if (clk && k < 10) F.phase_ns[1 + 3 * k] = F.phase_ns[2 + 3 * k] = F.phase_ns[3 + 3 * k] = global_ns();
+            continue;
+        }
+
+        // ---------------- phase S: sort the agents by state (stable: agents of one row stay in agent order).  The sort
+        // reads cur[] only, which phase A does not write; its own barriers also order phase A before the readers.
+        int src = 0;
+        for (int p = 0; p < X.passes; ++p) {
+            const bool last = p == X.passes - 1;
+            radix_pass<WARPS>(grid, s_whist, p == 0 ? cur : X.key[src], X.val[src], X.key[src ^ 1], X.val[src ^ 1], last ? X.rank : nullptr, n,
+                              p * kRadixBits, X.ghist, X.rowtot, p == 0);
+            src ^= 1;
+        }
+        const int32_t* skey = X.key[src];
+        const int32_t* perm = X.val[src];
+        // segment bounds per row; heads register their sequencer
+        for (int base = (tid & ~31); base < n; base += nthreads) {
+            const int p = base + lane;
+            bool head = false;
+            if (p < n) {
+                const int s = skey[p];
+                head = p == 0 || skey[p - 1] != s;
+                const bool tail = p == n - 1 || skey[p + 1] != s;
+                uint32_t* sg = X.seg + (size_t)s * 4;
+                if (head) { sg[0] = (uint32_t)p; sg[2] = epoch; sg[3] = (uint32_t)p; }
+                if (tail) sg[1] = (uint32_t)p + 1u;
+            }
+            const uint32_t hm = __ballot_sync(kFull, head);
+            if (lane == 0) X.hmask[base >> 5] = hm;
+        }
+        grid.sync();
+        if (clk && k < 10) F.phase_ns[1 + 3 * k] = global_ns();
+
+        // ---------------- phase R: readers
+        for (int base = (tid & ~31); base < n; base += nthreads) {
+            const int i = base + lane;
+            const bool active = i < n;
+            const int ii = active ? i : 0;
+            const uint8_t at = F.tr_a[ii];
+            const bool term = (at & 0x80) != 0;
+            const int a = at & 0x7F;
+            const float r = F.tr_r[ii];
+            const int y = nxt[ii];
+            const int q = X.rank[ii];
+            const bool boot = active && !term;
+            uint4 sg = make_uint4(0, 0, 0, 0);
+            if (boot) sg = __ldcg(reinterpret_cast<const uint4*>(X.seg + (size_t)y * 4));
+            RowGather<LPR> rows;
+            rows.issue(T, y, boot);
+            const bool has_writers = boot && sg.z == epoch;
+            int before = 0;  // writers of y that precede agent i
+            if (has_writers) {
+                int lo = (int)sg.x, hi = (int)sg.y;  // first position in [lo, hi) whose agent is >= i
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldcg(perm + mid) < i) lo = mid + 1; else hi = mid;
+                }
+                before = lo - (int)sg.x;
+            }
+            const uint32_t ew = (ENV == 1 && active) ? F.envw[ii] : 0u;
+            const uint32_t m2 = boot ? (F.use_masks ? env_mask<ENV>(y, ew, T.A, F.env_seed) : full) : 0u;
+            if (boot && m2 == 0u) atomicOr(T.err, kErrEmpty);
+            const float m_row = rows.row_max((boot && before == 0) ? m2 : 0u);
+            bool deferred = false;
+            if (active) {
+                if (!boot || before == 0) {
+                    const float t = td_target_s(r, term ? 0.0f : m_row, F.gamma);
+                    st_relaxed_u64(X.targ + q, ((uint64_t)((etag << 6) | (uint32_t)a) << 32) | (uint64_t)__float_as_uint(t));
+                } else {
+                    uint4 rec = make_uint4((uint32_t)((int)sg.x + before - 1), (uint32_t)q, __float_as_uint(r), (uint32_t)a);
+                    *reinterpret_cast<uint4*>(X.rrec + (size_t)i * 4) = rec;
+                    deferred = true;
+                }
+            }
+            const uint32_t dm = __ballot_sync(kFull, deferred);
+            if (lane == 0) X.rmask[base >> 5] = dm;
+        }
+        grid.sync();
+        if (clk && k < 10) F.phase_ns[2 + 3 * k] = global_ns();
+
+        // ---------------- phase Q: sequencers and deferred readers, non-blocking sweeps over statically owned tiles
+        {
+            bool seq_left = true, rd_left = true;
+            const uint64_t t_start = global_ns();
+            for (uint32_t spins = 0; seq_left || rd_left; ++spins) {
+                if (seq_left) {
+                    seq_left = false;
+                    for (int tile = gwarp; tile < ntiles; tile += nwarps) {
+                        const uint32_t hm = __ldcg(X.hmask + tile);
+                        if (hm == 0u) continue;
+                        bool fin = false;
+                        if ((hm >> lane) & 1u) {
+                            const int p0 = tile * 32 + lane;
+                            const int s = __ldcg(skey + p0);
+                            uint32_t* sg = X.seg + (size_t)s * 4;
+                            const int en = (int)__ldcg(sg + 1);
+                            int p = (int)__ldcg(sg + 3);
+                            float* row = T.q + (size_t)s * T.ld;
+                            const uint32_t legal = F.use_masks ? state_mask<ENV>(s, T.A, F.env_seed, full) : full;
+                            // is the next target there at all?  (cheap test before the row is loaded)
+                            uint64_t w = ld_relaxed_u64(X.targ + p);
+                            if ((uint32_t)(w >> 38) == etag) {
+#pragma unroll
+                                for (int c = 0; c < LPR; ++c) {
+                                    const F8 v8 = ld_row8(row + 8 * c);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) vals[(8 * c + j) * 256] = v8.v[j];
+                                }
+                                uint32_t touched = 0u;
+                                for (;;) {
+                                    const int a = (int)((w >> 32) & 63u);
+                                    const float v = td_from_target_s(vals[a * 256], __uint_as_float((uint32_t)w), lr);
+                                    vals[a * 256] = v;
+                                    touched |= 1u << a;
+                                    float mx = -INFINITY;
+                                    for (uint32_t bm = legal; bm; bm &= bm - 1u) mx = fmax_plain(mx, vals[(__ffs(bm) - 1) * 256]);
+                                    st_relaxed_u64(X.mhist + p, ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(mx));
+                                    ++p;
+                                    if (p == en) break;
+                                    w = ld_relaxed_u64(X.targ + p);
+                                    if ((uint32_t)(w >> 38) != etag) break;
+                                }
+                                for (uint32_t bm = touched; bm; bm &= bm - 1u) {  // commit / park the cells that changed
+                                    const int a = __ffs(bm) - 1;
+                                    row[a] = vals[a * 256];
+                                }
+                                if (p == en) fin = true; else __stcg(sg + 3, (uint32_t)p);
+                            }
+                        }
+                        const uint32_t done = __ballot_sync(kFull, fin);
+                        const uint32_t keep = hm & ~done;
+                        if (lane == 0 && keep != hm) __stcg(X.hmask + tile, keep);
+                        seq_left |= keep != 0u;
+                    }
+                }
+                if (rd_left) {
+                    rd_left = false;
+                    for (int tile = gwarp; tile < ntiles; tile += nwarps) {
+                        const uint32_t dm = __ldcg(X.rmask + tile);
+                        if (dm == 0u) continue;
+                        bool fin = false;
+                        if ((dm >> lane) & 1u) {
+                            const int i = tile * 32 + lane;
+                            const uint4 rec = __ldcg(reinterpret_cast<const uint4*>(X.rrec + (size_t)i * 4));
+                            const uint64_t w = ld_relaxed_u64(X.mhist + rec.x);
+                            if ((uint32_t)(w >> 32) == epoch) {
+                                const float t = td_target_s(__uint_as_float(rec.z), __uint_as_float((uint32_t)w), F.gamma);
+                                st_relaxed_u64(X.targ + rec.y, ((uint64_t)((etag << 6) | rec.w) << 32) | (uint64_t)__float_as_uint(t));
+                                fin = true;
+                            }
+                        }
+                        const uint32_t done = __ballot_sync(kFull, fin);
+                        const uint32_t keep = dm & ~done;
+                        if (lane == 0 && keep != dm) __stcg(X.rmask + tile, keep);
+                        rd_left |= keep != 0u;
+                    }
+                }
+                if ((spins & 63u) == 63u && global_ns() - t_start > kTimeoutNs) { atomicOr(T.err, kErrTimeout); break; }
+            }
+        }
+        grid.sync();
+        if (clk && k < 10) F.phase_ns[3 + 3 * k] = global_ns();
+    }
+    if (F.steps & 1) {
+        for (int i = tid; i < n; i += nthreads) F.st_a[i] = F.st_b[i];
+    }
+}
+
+}  // namespace qe
