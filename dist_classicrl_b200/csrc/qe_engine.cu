@@ -222,6 +222,19 @@ float* qe_table_ptr(qe_engine_t* e) { return e->q_real; }
 int32_t qe_table_stride(qe_engine_t* e) { return e->ld; }
 int64_t qe_kernel_launches(qe_engine_t* e) { return e->launches; }
 int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
+double qe_debug_gridsync_us(qe_engine_t* e, int32_t iters) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gridsync_probe_kernel, 256, 0) != cudaSuccess) return -1.0;
+    per_sm = per_sm > 4 ? 4 : per_sm;
+    int blocks = per_sm * e->sms;
+    uint64_t* d_out = e->phase_ns;
+    void* args[] = {&iters, &d_out};
+    if (cudaLaunchCooperativeKernel((void*)gridsync_probe_kernel, dim3(blocks), dim3(256), args, 0, 0) != cudaSuccess) return -1.0;
+    uint64_t ns = 0;
+    if (cudaMemcpy(&ns, d_out, sizeof(ns), cudaMemcpyDeviceToHost) != cudaSuccess) return -1.0;
+    return (double)ns / 1e3 / iters;
+}
 int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap) {
     std::lock_guard<std::mutex> lk(e->mu);
     uint64_t h[33];
@@ -577,6 +590,7 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     if (e->use_sorted && e->state_base == 0) {
         int rc = coop_blocks(e, fused_sorted_kernel<ENV, LPR>, (long long)F.n, &blocks);
         if (rc) return rc;
+        if (blocks > kSortMaxBlocks * kSortStride) blocks = kSortMaxBlocks * kSortStride;
         if (blocks > e->sorted_grid) {
             CK(cudaStreamSynchronize(st));
             cudaFree(e->X.ghist);

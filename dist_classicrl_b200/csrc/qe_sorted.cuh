@@ -25,8 +25,10 @@
 
 namespace qe {
 
-constexpr int kRadixBits = 8;
+constexpr int kRadixBits = 10;
 constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortStride = 4;        // every 4th block streams the keys of the sort
+constexpr int kSortMaxBlocks = 256;   // sorting blocks: the digit scan keeps one row of block counts in a warp's registers
 
 struct SortedScratch {
     int32_t* key[2];      // [cap] ping-pong keys (states)
@@ -69,65 +71,97 @@ __device__ __forceinline__ uint32_t state_mask(int s, int A, uint32_t env_seed, 
 // (one warp per digit); grid barrier; every warp walks its part in order, 32 keys at a time: position = digit base +
 // blocks before + warps before + earlier keys of the part + earlier lanes with the same digit (match.any).
 template <int WARPS>
-__device__ __forceinline__ void radix_pass(cg::grid_group& grid, int (*whist)[kRadix], const int32_t* kin, const int32_t* vin,
+__device__ __forceinline__ void radix_pass(cg::grid_group& grid, int (*whist)[kRadix], int* s_base, const int32_t* kin, const int32_t* vin,
                                            int32_t* kout, int32_t* vout, int32_t* rank_out, int n, int shift, int* ghist, int* rowtot,
                                            bool iota_vals) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nb = gridDim.x, b = blockIdx.x;
-    const int chunk = ((n + nb - 1) / nb + 31) & ~31;          // per block, multiple of 32
+    // One block in kSortStride streams the keys (the matrix of per-block digit counts, which is touched with a stride
+    // three times per pass, stays small); all blocks help with the digit scan.
+    const bool sorter = (blockIdx.x % kSortStride) == 0;
+    const int nb = (gridDim.x + kSortStride - 1) / kSortStride, b = blockIdx.x / kSortStride;
+    const int chunk = ((n + nb - 1) / nb + 31) & ~31;          // per sorting block, multiple of 32
     const int part = ((chunk / 32 + WARPS - 1) / WARPS) * 32;  // per warp, multiple of 32
-    const int lo = min(b * chunk + warp * part, n), hi = min(min(b * chunk + (warp + 1) * part, (b + 1) * chunk), n);
+    int lo = min(b * chunk + warp * part, n), hi = min(min(b * chunk + (warp + 1) * part, (b + 1) * chunk), n);
+    if (!sorter) lo = hi = 0;
     for (int d = lane; d < kRadix; d += 32) whist[warp][d] = 0;
     __syncwarp();
-    for (int base = lo; base < hi; base += 32) {
-        const int x = base + lane;
-        if (x < hi) atomicAdd(&whist[warp][((uint32_t)kin[x] >> shift) & (kRadix - 1)], 1);
+    for (int base = lo; base < hi; base += 128) {  // four loads in flight per lane
+        int32_t kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int x = base + 32 * u + lane;
+            kk[u] = x < hi ? kin[x] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (base + 32 * u + lane < hi) atomicAdd(&whist[warp][((uint32_t)kk[u] >> shift) & (kRadix - 1)], 1);
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
-        int t = 0;
+    if (sorter)
+        for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+            int t = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) t += whist[w][d];
-        ghist[d * nb + b] = t;
-    }
-    grid.sync();
-    {   // exclusive scan of every digit's row of block counts; one warp per digit
-        const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-        for (int d = gw; d < kRadix; d += nw) {
-            int carry = 0;
-            for (int base = 0; base < nb; base += 32) {
-                const int x = base + lane;
-                const int v = x < nb ? ghist[d * nb + x] : 0;
-                int incl = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= o) incl += y;
-                }
-                if (x < nb) ghist[d * nb + x] = carry + incl - v;
-                carry += __shfl_sync(kFull, incl, 31);
-            }
-            if (lane == 0) rowtot[d] = carry;
+            for (int w = 0; w < WARPS; ++w) t += whist[w][d];
+            ghist[d * nb + b] = t;
         }
-    }
     grid.sync();
-    // digit bases (every block redoes the 256-entry scan), then this warp's first free position per digit
-    __shared__ int s_base[kRadix];
-    if (threadIdx.x < 32) {
-        int carry = 0;
-        for (int base = 0; base < kRadix; base += 32) {
-            const int v = rowtot[base + lane];
-            int incl = v;
+    {   // exclusive scan of every digit's row of block counts; one warp per digit, the whole row in registers
+        const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+        constexpr int kPerLane = kSortMaxBlocks / 32;
+        const int per = (nb + 31) / 32;
+        for (int d = gw; d < kRadix; d += nw) {
+            int* row = ghist + d * nb;
+            int v[kPerLane];
+            int sum = 0;
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) {
+                const int x = lane * per + j;
+                v[j] = (j < per && x < nb) ? row[x] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) sum += v[j];
+            int incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int y = __shfl_up_sync(kFull, incl, o);
                 if (lane >= o) incl += y;
             }
-            s_base[base + lane] = carry + incl - v;
-            carry += __shfl_sync(kFull, incl, 31);
+            int run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) {
+                const int x = lane * per + j;
+                if (j < per && x < nb) row[x] = run;
+                run += v[j];
+            }
+            if (lane == 31) rowtot[d] = incl;
         }
     }
+    grid.sync();
+    // digit bases (every block redoes the scan of the digit totals), then this warp's first free position per digit
+    {
+        constexpr int kPer = kRadix / 256;  // digits per thread (blockDim.x == 256)
+        int v[kPer];
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) { v[j] = rowtot[threadIdx.x * kPer + j]; sum += v[j]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += y;
+        }
+        __shared__ int s_wsum[WARPS];
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) before += (w < warp) ? s_wsum[w] : 0;
+        int run = before + incl - sum;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) { s_base[threadIdx.x * kPer + j] = run; run += v[j]; }
+    }
     __syncthreads();
+    if (sorter)
     for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
         int run = s_base[d] + ghist[d * nb + b];
 #pragma unroll
@@ -138,24 +172,40 @@ __device__ __forceinline__ void radix_pass(cg::grid_group& grid, int (*whist)[kR
         }
     }
     __syncthreads();
-    for (int base = lo; base < hi; base += 32) {
-        const int x = base + lane;
-        const bool act = x < hi;
-        const int32_t k = act ? kin[x] : 0;
-        const uint32_t d = act ? (((uint32_t)k >> shift) & (kRadix - 1)) : (uint32_t)kRadix + lane;  // idle lanes match nobody
-        const uint32_t peers = __match_any_sync(kFull, d);
-        if (act) {
-            const int pos = whist[warp][d] + __popc(peers & ((1u << lane) - 1u));
-            const int32_t v = iota_vals ? x : vin[x];
-            kout[pos] = k;
-            vout[pos] = v;
-            if (rank_out) rank_out[v] = pos;
+    for (int base = lo; base < hi; base += 128) {
+        int32_t kk[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int x = base + 32 * u + lane;
+            kk[u] = x < hi ? kin[x] : 0;
+            vv[u] = x < hi ? (iota_vals ? x : vin[x]) : 0;
         }
-        __syncwarp();
-        if (act && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int x = base + 32 * u + lane;
+            const bool act = x < hi;
+            const uint32_t d = act ? (((uint32_t)kk[u] >> shift) & (kRadix - 1)) : (uint32_t)kRadix + lane;  // idle lanes match nobody
+            const uint32_t peers = __match_any_sync(kFull, d);
+            if (act) {
+                const int pos = whist[warp][d] + __popc(peers & ((1u << lane) - 1u));
+                kout[pos] = kk[u];
+                vout[pos] = vv[u];
+                if (rank_out) rank_out[vv[u]] = pos;
+            }
+            __syncwarp();
+            if (act && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
+            __syncwarp();
+        }
     }
     grid.sync();
+}
+
+// development aid: cost of one grid barrier at the fused loop's launch shape
+__global__ void __launch_bounds__(256, 4) gridsync_probe_kernel(int iters, uint64_t* out) {
+    cg::grid_group grid = cg::this_grid();
+    const uint64_t t0 = global_ns();
+    for (int i = 0; i < iters; ++i) grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = global_ns() - t0;
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -165,8 +215,12 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
     constexpr int WARPS = 8;
     __shared__ double s_sum[8];
     __shared__ unsigned int s_cnt[8];
-    __shared__ int s_whist[WARPS][kRadix];       // radix sort
-    __shared__ float s_vals[8 * LPR * 256];      // sequencers: the row being walked, one column per thread
+    // the sort (per-warp digit counters) and the sequencers (one row per thread) never run at the same time
+    constexpr int kSortWords = WARPS * kRadix, kValWords = 8 * LPR * 256;
+    __shared__ int s_union[kSortWords > kValWords ? kSortWords : kValWords];
+    __shared__ int s_base[kRadix];
+    int (*s_whist)[kRadix] = reinterpret_cast<int (*)[kRadix]>(s_union);
+    float* s_vals = reinterpret_cast<float*>(s_union);
     const int lane = threadIdx.x & 31;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
@@ -270,7 +324,7 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
         int src = 0;
         for (int p = 0; p < X.passes; ++p) {
             const bool last = p == X.passes - 1;
-            radix_pass<WARPS>(grid, s_whist, p == 0 ? cur : X.key[src], X.val[src], X.key[src ^ 1], X.val[src ^ 1], last ? X.rank : nullptr, n,
+            radix_pass<WARPS>(grid, s_whist, s_base, p == 0 ? cur : X.key[src], X.val[src], X.key[src ^ 1], X.val[src ^ 1], last ? X.rank : nullptr, n,
                               p * kRadixBits, X.ghist, X.rowtot, p == 0);
             src ^= 1;
         }

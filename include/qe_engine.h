@@ -177,6 +177,8 @@ int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch
  * of the first 10 vector steps the time after phase A (select + env step + writer registration), after phase B1 (TD
  * update, first pass) and after phase B2 (TD update, deferred agents).  Returns the number of values written. */
 int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap);
+/* development aid: microseconds per grid-wide barrier at the fused loop's launch shape (cooperative launch, 4 CTAs/SM) */
+double qe_debug_gridsync_us(qe_engine_t* e, int32_t iters);
 const char* qe_build_info(void);
 
 #ifdef __cplusplus
