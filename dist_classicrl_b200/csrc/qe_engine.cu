@@ -88,7 +88,8 @@ static int ensure_agents(qe_engine* e, int n) {
     {
         SortedScratch& X = e->X;
         for (int b = 0; b < 2; ++b) { cudaFree(X.key[b]); cudaFree(X.val[b]); }
-        cudaFree(X.rank); cudaFree(X.targ); cudaFree(X.mhist); cudaFree(X.rrec); cudaFree(X.rmask); cudaFree(X.hmask);
+        cudaFree(X.rank); cudaFree(X.targ); cudaFree(X.mhist); cudaFree(X.rrec); cudaFree(X.rmask); cudaFree(X.hmask); cudaFree(X.hrec);
+        CK(cudaMalloc(&X.hrec, sizeof(uint32_t) * 4 * (size_t)cap));
         for (int b = 0; b < 2; ++b) {
             CK(cudaMalloc(&X.key[b], sizeof(int32_t) * cap));
             CK(cudaMalloc(&X.val[b], sizeof(int32_t) * cap));
@@ -209,7 +210,7 @@ int qe_destroy(qe_engine_t* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (int b = 0; b < 2; ++b) { cudaFree(e->X.key[b]); cudaFree(e->X.val[b]); }
-    cudaFree(e->X.rank); cudaFree(e->X.targ); cudaFree(e->X.mhist); cudaFree(e->X.rrec); cudaFree(e->X.rmask); cudaFree(e->X.hmask);
+    cudaFree(e->X.rank); cudaFree(e->X.targ); cudaFree(e->X.mhist); cudaFree(e->X.rrec); cudaFree(e->X.rmask); cudaFree(e->X.hmask); cudaFree(e->X.hrec);
     cudaFree(e->X.seg); cudaFree(e->X.rowtot); cudaFree(e->X.ghist);
     cudaFree(e->q_real); cudaFree(e->T.later_buf); cudaFree(e->T.spill); cudaFree(e->T.spill_next); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);

@@ -38,10 +38,11 @@ struct SortedScratch {
     int32_t* rank;        // [cap] sorted position of every agent
     uint64_t* targ;       // [cap] by sorted position: (epoch << 6 | action) << 32 | target bits
     uint64_t* mhist;      // [cap] by sorted position: epoch << 32 | masked row max after this writer
-    uint32_t* seg;        // [S][4] per state: {segment start, segment end, epoch of both, sequencer progress}
+    uint32_t* seg;        // [S][4] per state: {segment start, segment end, epoch of both, -}
     uint32_t* rrec;       // [cap][4] deferred readers: {mhist position, own sorted position, reward bits, action}
     uint32_t* rmask;      // [cap/32] per agent tile: deferred readers
     uint32_t* hmask;      // [cap/32] per tile of sorted positions: segment heads whose sequencer has not finished
+    uint32_t* hrec;       // [cap][4] at a segment's head position: {state, segment end, sequencer progress, -}
     int passes;           // radix passes needed for the state range
 };
 
@@ -330,17 +331,24 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
         }
         const int32_t* skey = X.key[src];
         const int32_t* perm = X.val[src];
-        // segment bounds per row; heads register their sequencer
+        // segment bounds per row: the head of every segment finds its end (gallop + binary search over the sorted keys)
         for (int base = (tid & ~31); base < n; base += nthreads) {
             const int p = base + lane;
             bool head = false;
             if (p < n) {
                 const int s = skey[p];
                 head = p == 0 || skey[p - 1] != s;
-                const bool tail = p == n - 1 || skey[p + 1] != s;
-                uint32_t* sg = X.seg + (size_t)s * 4;
-                if (head) { sg[0] = (uint32_t)p; sg[2] = epoch; sg[3] = (uint32_t)p; }
-                if (tail) sg[1] = (uint32_t)p + 1u;
+                if (head) {
+                    int lo = p + 1, step = 1;  // invariant: skey[lo - 1] == s
+                    while (lo < n && __ldcg(skey + min(lo + step - 1, n - 1)) == s && lo + step - 1 < n) { lo += step; step <<= 1; }
+                    int hi = min(lo + step - 1, n);  // first position known (or assumed, at n) to differ is in (lo-1, hi]
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (__ldcg(skey + mid) == s) lo = mid + 1; else hi = mid;
+                    }
+                    *reinterpret_cast<uint4*>(X.seg + (size_t)s * 4) = make_uint4((uint32_t)p, (uint32_t)lo, epoch, 0u);
+                    *reinterpret_cast<uint4*>(X.hrec + (size_t)p * 4) = make_uint4((uint32_t)s, (uint32_t)lo, (uint32_t)p, 0u);
+                }
             }
             const uint32_t hm = __ballot_sync(kFull, head);
             if (lane == 0) X.hmask[base >> 5] = hm;
@@ -396,80 +404,140 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
         if (clk && k < 10) F.phase_ns[2 + 3 * k] = global_ns();
 
         // ---------------- phase Q: sequencers and deferred readers, non-blocking sweeps over statically owned tiles
+        // Warp w owns tiles w, w + nwarps, ...; lane t keeps the pending masks of the t-th owned tile in registers and
+        // the pending jobs of all owned tiles are compacted into batches of 32 (one job per lane), so a sweep costs as
+        // many round trips as there are batches, not as there are tiles.  (A warp that owns more than 32 tiles walks
+        // them one by one with the masks in memory.)
         {
+            const int owned = (ntiles - gwarp + nwarps - 1) / nwarps;  // may be <= 0
+            const bool in_regs = owned <= 32;
+            uint32_t my_h = 0u, my_r = 0u;
+            if (in_regs && lane < owned) {
+                my_h = __ldcg(X.hmask + gwarp + lane * nwarps);
+                my_r = __ldcg(X.rmask + gwarp + lane * nwarps);
+            }
+            // one sequencer job: walk the segment whose head sits at sorted position p0 while targets are there
+            auto sequencer = [&](int p0) -> bool {
+                uint32_t* hr = X.hrec + (size_t)p0 * 4;
+                const uint4 h4 = __ldcg(reinterpret_cast<const uint4*>(hr));
+                const int s = (int)h4.x, en = (int)h4.y;
+                int p = (int)h4.z;
+                uint64_t w = ld_relaxed_u64(X.targ + p);  // is the next target there at all?  (before the row is loaded)
+                if ((uint32_t)(w >> 38) != etag) return false;
+                float* row = T.q + (size_t)s * T.ld;
+                const uint32_t legal = F.use_masks ? state_mask<ENV>(s, T.A, F.env_seed, full) : full;
+#pragma unroll
+                for (int c = 0; c < LPR; ++c) {
+                    const F8 v8 = ld_row8(row + 8 * c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) vals[(8 * c + j) * 256] = v8.v[j];
+                }
+                uint32_t touched = 0u;
+                // running masked row max and one action that attains it (recomputed only when that cell goes down)
+                float mx = -INFINITY;
+                int amx = 0;
+                for (uint32_t bm = legal; bm; bm &= bm - 1u) {
+                    const int a2 = __ffs(bm) - 1;
+                    const float x = vals[a2 * 256];
+                    if (x > mx) { mx = x; amx = a2; }
+                }
+                bool more = true;
+                while (more) {
+                    // up to eight targets per round trip (the first one is known to be there)
+                    uint64_t wv[8];
+                    wv[0] = w;
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) wv[j] = (p + j < en) ? ld_relaxed_u64(X.targ + p + j) : 0ull;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!more) break;
+                        if (j > 0 && (p == en || (uint32_t)(wv[j] >> 38) != etag)) { more = false; break; }
+                        const int a = (int)((wv[j] >> 32) & 63u);
+                        const float v = td_from_target_s(vals[a * 256], __uint_as_float((uint32_t)wv[j]), lr);
+                        vals[a * 256] = v;
+                        touched |= 1u << a;
+                        if (v >= mx) { mx = v; amx = a; }
+                        else if (a == amx) {
+                            mx = -INFINITY;
+                            for (uint32_t bm = legal; bm; bm &= bm - 1u) {
+                                const int a2 = __ffs(bm) - 1;
+                                const float x = vals[a2 * 256];
+                                if (x > mx) { mx = x; amx = a2; }
+                            }
+                        }
+                        st_relaxed_u64(X.mhist + p, ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(mx));
+                        ++p;
+                    }
+                    if (more) {  // all eight consumed: is there a ninth?
+                        if (p == en) break;
+                        w = ld_relaxed_u64(X.targ + p);
+                        if ((uint32_t)(w >> 38) != etag) break;
+                    }
+                }
+                for (uint32_t bm = touched; bm; bm &= bm - 1u) {  // commit / park the cells that changed
+                    const int a = __ffs(bm) - 1;
+                    row[a] = vals[a * 256];
+                }
+                if (p == en) return true;
+                __stcg(hr + 2, (uint32_t)p);
+                return false;
+            };
+            // one deferred reader: the row max it waits for has been published -> deposit the target
+            auto reader = [&](int i) -> bool {
+                const uint4 rec = __ldcg(reinterpret_cast<const uint4*>(X.rrec + (size_t)i * 4));
+                const uint64_t w = ld_relaxed_u64(X.mhist + rec.x);
+                if ((uint32_t)(w >> 32) != epoch) return false;
+                const float tg = td_target_s(__uint_as_float(rec.z), __uint_as_float((uint32_t)w), F.gamma);
+                st_relaxed_u64(X.targ + rec.y, ((uint64_t)((etag << 6) | rec.w) << 32) | (uint64_t)__float_as_uint(tg));
+                return true;
+            };
+            // one sweep over the compacted pending jobs of `mine`; returns the updated mask register
+            auto sweep = [&](uint32_t mine, auto job) -> uint32_t {
+                DeferredGroup grp;
+                grp.init(mine);
+                for (int b0 = 0; b0 < grp.total; b0 += 32) {
+                    const int rank = b0 + lane;
+                    const bool act = rank < grp.total;
+                    const int rel = grp.agent_of(act ? rank : 0);  // (owned tile index) * 32 + lane-in-tile
+                    bool fin = false;
+                    if (act) fin = job((gwarp + (rel >> 5) * nwarps) * 32 + (rel & 31));
+                    const int t_lo = __shfl_sync(kFull, rel >> 5, 0);
+                    const int t_hi = __shfl_sync(kFull, rel >> 5, min(grp.total - b0, 32) - 1);
+                    for (int t = t_lo; t <= t_hi; ++t) {
+                        const uint32_t bits = __reduce_or_sync(kFull, (fin && (rel >> 5) == t) ? (1u << (rel & 31)) : 0u);
+                        if (lane == t) mine &= ~bits;
+                    }
+                }
+                return mine;
+            };
             bool seq_left = true, rd_left = true;
             const uint64_t t_start = global_ns();
             for (uint32_t spins = 0; seq_left || rd_left; ++spins) {
-                if (seq_left) {
-                    seq_left = false;
-                    for (int tile = gwarp; tile < ntiles; tile += nwarps) {
-                        const uint32_t hm = __ldcg(X.hmask + tile);
-                        if (hm == 0u) continue;
-                        bool fin = false;
-                        if ((hm >> lane) & 1u) {
-                            const int p0 = tile * 32 + lane;
-                            const int s = __ldcg(skey + p0);
-                            uint32_t* sg = X.seg + (size_t)s * 4;
-                            const int en = (int)__ldcg(sg + 1);
-                            int p = (int)__ldcg(sg + 3);
-                            float* row = T.q + (size_t)s * T.ld;
-                            const uint32_t legal = F.use_masks ? state_mask<ENV>(s, T.A, F.env_seed, full) : full;
-                            // is the next target there at all?  (cheap test before the row is loaded)
-                            uint64_t w = ld_relaxed_u64(X.targ + p);
-                            if ((uint32_t)(w >> 38) == etag) {
-#pragma unroll
-                                for (int c = 0; c < LPR; ++c) {
-                                    const F8 v8 = ld_row8(row + 8 * c);
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) vals[(8 * c + j) * 256] = v8.v[j];
-                                }
-                                uint32_t touched = 0u;
-                                for (;;) {
-                                    const int a = (int)((w >> 32) & 63u);
-                                    const float v = td_from_target_s(vals[a * 256], __uint_as_float((uint32_t)w), lr);
-                                    vals[a * 256] = v;
-                                    touched |= 1u << a;
-                                    float mx = -INFINITY;
-                                    for (uint32_t bm = legal; bm; bm &= bm - 1u) mx = fmax_plain(mx, vals[(__ffs(bm) - 1) * 256]);
-                                    st_relaxed_u64(X.mhist + p, ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(mx));
-                                    ++p;
-                                    if (p == en) break;
-                                    w = ld_relaxed_u64(X.targ + p);
-                                    if ((uint32_t)(w >> 38) != etag) break;
-                                }
-                                for (uint32_t bm = touched; bm; bm &= bm - 1u) {  // commit / park the cells that changed
-                                    const int a = __ffs(bm) - 1;
-                                    row[a] = vals[a * 256];
-                                }
-                                if (p == en) fin = true; else __stcg(sg + 3, (uint32_t)p);
-                            }
+                if (in_regs) {
+                    if (seq_left) { my_h = sweep(my_h, sequencer); seq_left = __any_sync(kFull, my_h != 0u); }
+                    if (rd_left) { my_r = sweep(my_r, reader); rd_left = __any_sync(kFull, my_r != 0u); }
+                } else {
+                    if (seq_left) {
+                        seq_left = false;
+                        for (int tile = gwarp; tile < ntiles; tile += nwarps) {
+                            const uint32_t hm = __ldcg(X.hmask + tile);
+                            if (hm == 0u) continue;
+                            const bool fin = ((hm >> lane) & 1u) ? sequencer(tile * 32 + lane) : false;
+                            const uint32_t keep = hm & ~__ballot_sync(kFull, fin);
+                            if (lane == 0 && keep != hm) __stcg(X.hmask + tile, keep);
+                            seq_left |= keep != 0u;
                         }
-                        const uint32_t done = __ballot_sync(kFull, fin);
-                        const uint32_t keep = hm & ~done;
-                        if (lane == 0 && keep != hm) __stcg(X.hmask + tile, keep);
-                        seq_left |= keep != 0u;
                     }
-                }
-                if (rd_left) {
-                    rd_left = false;
-                    for (int tile = gwarp; tile < ntiles; tile += nwarps) {
-                        const uint32_t dm = __ldcg(X.rmask + tile);
-                        if (dm == 0u) continue;
-                        bool fin = false;
-                        if ((dm >> lane) & 1u) {
-                            const int i = tile * 32 + lane;
-                            const uint4 rec = __ldcg(reinterpret_cast<const uint4*>(X.rrec + (size_t)i * 4));
-                            const uint64_t w = ld_relaxed_u64(X.mhist + rec.x);
-                            if ((uint32_t)(w >> 32) == epoch) {
-                                const float t = td_target_s(__uint_as_float(rec.z), __uint_as_float((uint32_t)w), F.gamma);
-                                st_relaxed_u64(X.targ + rec.y, ((uint64_t)((etag << 6) | rec.w) << 32) | (uint64_t)__float_as_uint(t));
-                                fin = true;
-                            }
+                    if (rd_left) {
+                        rd_left = false;
+                        for (int tile = gwarp; tile < ntiles; tile += nwarps) {
+                            const uint32_t dm = __ldcg(X.rmask + tile);
+                            if (dm == 0u) continue;
+                            const bool fin = ((dm >> lane) & 1u) ? reader(tile * 32 + lane) : false;
+                            const uint32_t keep = dm & ~__ballot_sync(kFull, fin);
+                            if (lane == 0 && keep != dm) __stcg(X.rmask + tile, keep);
+                            rd_left |= keep != 0u;
                         }
-                        const uint32_t done = __ballot_sync(kFull, fin);
-                        const uint32_t keep = dm & ~done;
-                        if (lane == 0 && keep != dm) __stcg(X.rmask + tile, keep);
-                        rd_left |= keep != 0u;
                     }
                 }
                 if ((spins & 63u) == 63u && global_ns() - t_start > kTimeoutNs) { atomicOr(T.err, kErrTimeout); break; }
