@@ -416,71 +416,92 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
                 my_h = __ldcg(X.hmask + gwarp + lane * nwarps);
                 my_r = __ldcg(X.rmask + gwarp + lane * nwarps);
             }
-            // one sequencer job: walk the segment whose head sits at sorted position p0 while targets are there
-            auto sequencer = [&](int p0) -> bool {
-                uint32_t* hr = X.hrec + (size_t)p0 * 4;
-                const uint4 h4 = __ldcg(reinterpret_cast<const uint4*>(hr));
-                const int s = (int)h4.x, en = (int)h4.y;
-                int p = (int)h4.z;
-                uint64_t w = ld_relaxed_u64(X.targ + p);  // is the next target there at all?  (before the row is loaded)
-                if ((uint32_t)(w >> 38) != etag) return false;
-                float* row = T.q + (size_t)s * T.ld;
-                const uint32_t legal = F.use_masks ? state_mask<ENV>(s, T.A, F.env_seed, full) : full;
+            // A sequencer walks the segment of one row in agent order while targets are there.
+            struct Seq {
+                int s, en, p, amx;
+                uint32_t legal, touched;
+                float mx;
+                bool loaded;
+            };
+            auto seq_load_row = [&](Seq& q) {
+                const float* row = T.q + (size_t)q.s * T.ld;
 #pragma unroll
                 for (int c = 0; c < LPR; ++c) {
                     const F8 v8 = ld_row8(row + 8 * c);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) vals[(8 * c + j) * 256] = v8.v[j];
                 }
-                uint32_t touched = 0u;
-                // running masked row max and one action that attains it (recomputed only when that cell goes down)
-                float mx = -INFINITY;
-                int amx = 0;
-                for (uint32_t bm = legal; bm; bm &= bm - 1u) {
+                q.mx = -INFINITY;  // running masked row max and one action that attains it
+                q.amx = 0;
+                for (uint32_t bm = q.legal; bm; bm &= bm - 1u) {
                     const int a2 = __ffs(bm) - 1;
                     const float x = vals[a2 * 256];
-                    if (x > mx) { mx = x; amx = a2; }
+                    if (x > q.mx) { q.mx = x; q.amx = a2; }
                 }
+                q.loaded = true;
+            };
+            // consume the run of deposited targets that starts with w (= targ[q.p], known to be there); true = segment done
+            auto seq_advance = [&](Seq& q, uint64_t w) -> bool {
                 bool more = true;
                 while (more) {
-                    // up to eight targets per round trip (the first one is known to be there)
-                    uint64_t wv[8];
+                    uint64_t wv[8];  // up to eight targets per round trip
                     wv[0] = w;
 #pragma unroll
-                    for (int j = 1; j < 8; ++j) wv[j] = (p + j < en) ? ld_relaxed_u64(X.targ + p + j) : 0ull;
+                    for (int j = 1; j < 8; ++j) wv[j] = (q.p + j < q.en) ? ld_relaxed_u64(X.targ + q.p + j) : 0ull;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (!more) break;
-                        if (j > 0 && (p == en || (uint32_t)(wv[j] >> 38) != etag)) { more = false; break; }
+                        if (j > 0 && (q.p == q.en || (uint32_t)(wv[j] >> 38) != etag)) { more = false; break; }
                         const int a = (int)((wv[j] >> 32) & 63u);
                         const float v = td_from_target_s(vals[a * 256], __uint_as_float((uint32_t)wv[j]), lr);
                         vals[a * 256] = v;
-                        touched |= 1u << a;
-                        if (v >= mx) { mx = v; amx = a; }
-                        else if (a == amx) {
-                            mx = -INFINITY;
-                            for (uint32_t bm = legal; bm; bm &= bm - 1u) {
+                        q.touched |= 1u << a;
+                        if (v >= q.mx) { q.mx = v; q.amx = a; }
+                        else if (a == q.amx) {  // the cell that held the max went down: look again
+                            q.mx = -INFINITY;
+                            for (uint32_t bm = q.legal; bm; bm &= bm - 1u) {
                                 const int a2 = __ffs(bm) - 1;
                                 const float x = vals[a2 * 256];
-                                if (x > mx) { mx = x; amx = a2; }
+                                if (x > q.mx) { q.mx = x; q.amx = a2; }
                             }
                         }
-                        st_relaxed_u64(X.mhist + p, ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(mx));
-                        ++p;
+                        st_relaxed_u64(X.mhist + q.p, ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(q.mx));
+                        ++q.p;
                     }
                     if (more) {  // all eight consumed: is there a ninth?
-                        if (p == en) break;
-                        w = ld_relaxed_u64(X.targ + p);
+                        if (q.p == q.en) break;
+                        w = ld_relaxed_u64(X.targ + q.p);
                         if ((uint32_t)(w >> 38) != etag) break;
                     }
                 }
-                for (uint32_t bm = touched; bm; bm &= bm - 1u) {  // commit / park the cells that changed
+                return q.p == q.en;
+            };
+            auto seq_store_row = [&](Seq& q) {  // commit (or park) the cells that changed
+                float* row = T.q + (size_t)q.s * T.ld;
+                for (uint32_t bm = q.touched; bm; bm &= bm - 1u) {
                     const int a = __ffs(bm) - 1;
                     row[a] = vals[a * 256];
                 }
-                if (p == en) return true;
-                __stcg(hr + 2, (uint32_t)p);
-                return false;
+                q.touched = 0u;
+            };
+            auto seq_open = [&](int p0) -> Seq {
+                const uint4 h4 = __ldcg(reinterpret_cast<const uint4*>(X.hrec + (size_t)p0 * 4));
+                Seq q;
+                q.s = (int)h4.x; q.en = (int)h4.y; q.p = (int)h4.z;
+                q.legal = F.use_masks ? state_mask<ENV>(q.s, T.A, F.env_seed, full) : full;
+                q.touched = 0u; q.mx = 0.0f; q.amx = 0; q.loaded = false;
+                return q;
+            };
+            // one visit of a swept sequencer job
+            auto sequencer = [&](int p0) -> bool {
+                Seq q = seq_open(p0);
+                const uint64_t w = ld_relaxed_u64(X.targ + q.p);  // is the next target there at all?  (before the row is loaded)
+                if ((uint32_t)(w >> 38) != etag) return false;
+                seq_load_row(q);
+                const bool fin = seq_advance(q, w);
+                seq_store_row(q);
+                if (!fin) __stcg(X.hrec + (size_t)p0 * 4 + 2, (uint32_t)q.p);
+                return fin;
             };
             // one deferred reader: the row max it waits for has been published -> deposit the target
             auto reader = [&](int i) -> bool {
@@ -516,6 +537,42 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
                 if (in_regs) {
                     if (seq_left) { my_h = sweep(my_h, sequencer); seq_left = __any_sync(kFull, my_h != 0u); }
                     if (rd_left) { my_r = sweep(my_r, reader); rd_left = __any_sync(kFull, my_r != 0u); }
+                    // Few jobs left: they move into the lanes (sequencers first, then readers) and are polled back to
+                    // back -- a sequencer keeps its row in shared memory, a reader its two positions in registers.
+                    const int nh = (int)__reduce_add_sync(kFull, (uint32_t)__popc(my_h)), nr = (int)__reduce_add_sync(kFull, (uint32_t)__popc(my_r));
+                    if (nh + nr > 0 && nh + nr <= 32) {
+                        DeferredGroup gh, gr;
+                        gh.init(my_h);
+                        gr.init(my_r);
+                        const int relh = gh.agent_of(lane < nh ? lane : 0), relr = gr.agent_of((lane >= nh && lane < nh + nr) ? lane - nh : 0);
+                        int kind = lane < nh ? 2 : (lane < nh + nr ? 1 : 0);
+                        Seq q;
+                        q.s = q.en = q.p = q.amx = 0; q.legal = q.touched = 0u; q.mx = 0.0f; q.loaded = false;
+                        uint32_t mpos = 0u, tpos = 0u, rbits = 0u, ract = 0u;
+                        if (kind == 2) q = seq_open((gwarp + (relh >> 5) * nwarps) * 32 + (relh & 31));
+                        if (kind == 1) {
+                            const uint4 rec = __ldcg(reinterpret_cast<const uint4*>(X.rrec + (size_t)((gwarp + (relr >> 5) * nwarps) * 32 + (relr & 31)) * 4));
+                            mpos = rec.x; tpos = rec.y; rbits = rec.z; ract = rec.w;
+                        }
+                        for (uint32_t it = 0; __any_sync(kFull, kind != 0); ++it) {
+                            if (kind == 1) {
+                                const uint64_t w = ld_relaxed_u64(X.mhist + mpos);
+                                if ((uint32_t)(w >> 32) == epoch) {
+                                    const float tg = td_target_s(__uint_as_float(rbits), __uint_as_float((uint32_t)w), F.gamma);
+                                    st_relaxed_u64(X.targ + tpos, ((uint64_t)((etag << 6) | ract) << 32) | (uint64_t)__float_as_uint(tg));
+                                    kind = 0;
+                                }
+                            } else if (kind == 2) {
+                                const uint64_t w = ld_relaxed_u64(X.targ + q.p);
+                                if ((uint32_t)(w >> 38) == etag) {
+                                    if (!q.loaded) seq_load_row(q);
+                                    if (seq_advance(q, w)) { seq_store_row(q); kind = 0; }
+                                }
+                            }
+                            if ((it & 1023u) == 1023u && global_ns() - t_start > kTimeoutNs) { atomicOr(T.err, kErrTimeout); break; }
+                        }
+                        seq_left = rd_left = false;
+                    }
                 } else {
                     if (seq_left) {
                         seq_left = false;
