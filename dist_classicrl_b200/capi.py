@@ -75,6 +75,7 @@ SIGNATURES = {
     "qe_fused_grid_blocks": (i32, [vp]),
     "qe_fused_phase_ns": (i32, [vp, vp, i32]),
     "qe_debug_gridsync_us": (C.c_double, [vp, i32]),
+    "qe_debug_counters": (C.c_int, [vp, vp, i32]),
     "qe_build_info": (C.c_char_p, []),
 }
 

@@ -188,6 +188,8 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
         CK(cudaMalloc(&e->X.seg, sizeof(uint32_t) * 4 * (size_t)e->S));
         CK(cudaMemset(e->X.seg, 0, sizeof(uint32_t) * 4 * (size_t)e->S));
         CK(cudaMalloc(&e->X.rowtot, sizeof(int) * kRadix));
+        CK(cudaMalloc(&e->X.dbg, sizeof(unsigned long long) * 8));
+        CK(cudaMemset(e->X.dbg, 0, sizeof(unsigned long long) * 8));
         int bits = 1;
         while (bits < 31 && (1ll << bits) < e->S) ++bits;
         e->X.passes = (bits + kRadixBits - 1) / kRadixBits;
@@ -211,7 +213,7 @@ int qe_destroy(qe_engine_t* e) {
     cudaDeviceSynchronize();
     for (int b = 0; b < 2; ++b) { cudaFree(e->X.key[b]); cudaFree(e->X.val[b]); }
     cudaFree(e->X.rank); cudaFree(e->X.targ); cudaFree(e->X.mhist); cudaFree(e->X.rrec); cudaFree(e->X.rmask); cudaFree(e->X.hmask); cudaFree(e->X.hrec);
-    cudaFree(e->X.seg); cudaFree(e->X.rowtot); cudaFree(e->X.ghist);
+    cudaFree(e->X.seg); cudaFree(e->X.rowtot); cudaFree(e->X.dbg); cudaFree(e->X.ghist);
     cudaFree(e->q_real); cudaFree(e->T.later_buf); cudaFree(e->T.spill); cudaFree(e->T.spill_next); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
     delete e;
@@ -223,6 +225,13 @@ float* qe_table_ptr(qe_engine_t* e) { return e->q_real; }
 int32_t qe_table_stride(qe_engine_t* e) { return e->ld; }
 int64_t qe_kernel_launches(qe_engine_t* e) { return e->launches; }
 int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
+int qe_debug_counters(qe_engine_t* e, uint64_t* out8_host, int32_t reset) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->X.dbg) return fail(QE_ERR_ARG, "no counters");
+    CK(cudaMemcpy(out8_host, e->X.dbg, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(e->X.dbg, 0, 8 * sizeof(uint64_t)));
+    return QE_OK;
+}
 double qe_debug_gridsync_us(qe_engine_t* e, int32_t iters) {
     std::lock_guard<std::mutex> lk(e->mu);
     int per_sm = 0;

@@ -44,6 +44,7 @@ struct SortedScratch {
     uint32_t* hmask;      // [cap/32] per tile of sorted positions: segment heads whose sequencer has not finished
     uint32_t* hrec;       // [cap][4] at a segment's head position: {state, segment end, sequencer progress, -}
     int passes;           // radix passes needed for the state range
+    unsigned long long* dbg;  // [8] development counters (phase Q), accumulated over the launch
 };
 
 __device__ __forceinline__ uint32_t ttt_mask_of_state(int s) {  // empty cells of the board a base-3 state id encodes
@@ -541,6 +542,14 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
                     // back -- a sequencer keeps its row in shared memory, a reader its two positions in registers.
                     const int nh = (int)__reduce_add_sync(kFull, (uint32_t)__popc(my_h)), nr = (int)__reduce_add_sync(kFull, (uint32_t)__popc(my_r));
                     if (nh + nr > 0 && nh + nr <= 32) {
+                        const uint64_t t_res = global_ns();
+                        if (lane == 0 && X.dbg) {
+                            atomicAdd(X.dbg + 0, (unsigned long long)spins + 1ull);
+                            atomicAdd(X.dbg + 1, (unsigned long long)(t_res - t_start));
+                            atomicMax(X.dbg + 2, (unsigned long long)(t_res - t_start));
+                            atomicAdd(X.dbg + 5, 1ull);
+                            atomicAdd(X.dbg + 6, (unsigned long long)(nh + nr));
+                        }
                         DeferredGroup gh, gr;
                         gh.init(my_h);
                         gr.init(my_r);
@@ -548,7 +557,7 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
                         int kind = lane < nh ? 2 : (lane < nh + nr ? 1 : 0);
                         Seq q;
                         q.s = q.en = q.p = q.amx = 0; q.legal = q.touched = 0u; q.mx = 0.0f; q.loaded = false;
-                        uint32_t mpos = 0u, tpos = 0u, rbits = 0u, ract = 0u;
+                        uint32_t mpos = 0u, tpos = 0u, rbits = 0u, ract = 0u, wmpos = 0xFFFFFFFFu;
                         if (kind == 2) q = seq_open((gwarp + (relh >> 5) * nwarps) * 32 + (relh & 31));
                         if (kind == 1) {
                             const uint4 rec = __ldcg(reinterpret_cast<const uint4*>(X.rrec + (size_t)((gwarp + (relr >> 5) * nwarps) * 32 + (relr & 31)) * 4));
@@ -563,8 +572,22 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
                                     kind = 0;
                                 }
                             } else if (kind == 2) {
-                                const uint64_t w = ld_relaxed_u64(X.targ + q.p);
+                                uint64_t w = ld_relaxed_u64(X.targ + q.p);
+                                if ((uint32_t)(w >> 38) != etag) {
+                                    // The writer at q.p is a deferred reader.  Do not wait for its own deposit: fetch its
+                                    // record once and poll the row max it waits for -- one hop per level instead of two.
+                                    if (wmpos == 0xFFFFFFFFu) {
+                                        const uint4 rec = __ldcg(reinterpret_cast<const uint4*>(X.rrec + (size_t)__ldcg(perm + q.p) * 4));
+                                        wmpos = rec.x; rbits = rec.z; ract = rec.w;
+                                    }
+                                    const uint64_t mw = ld_relaxed_u64(X.mhist + wmpos);
+                                    if ((uint32_t)(mw >> 32) == epoch) {
+                                        const float tg = td_target_s(__uint_as_float(rbits), __uint_as_float((uint32_t)mw), F.gamma);
+                                        w = ((uint64_t)((etag << 6) | ract) << 32) | (uint64_t)__float_as_uint(tg);
+                                    }
+                                }
                                 if ((uint32_t)(w >> 38) == etag) {
+                                    wmpos = 0xFFFFFFFFu;
                                     if (!q.loaded) seq_load_row(q);
                                     if (seq_advance(q, w)) { seq_store_row(q); kind = 0; }
                                 }
@@ -572,6 +595,10 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
                             if ((it & 1023u) == 1023u && global_ns() - t_start > kTimeoutNs) { atomicOr(T.err, kErrTimeout); break; }
                         }
                         seq_left = rd_left = false;
+                        if (lane == 0 && X.dbg) {
+                            atomicAdd(X.dbg + 3, (unsigned long long)(global_ns() - t_res));
+                            atomicMax(X.dbg + 4, (unsigned long long)(global_ns() - t_res));
+                        }
                     }
                 } else {
                     if (seq_left) {

@@ -179,6 +179,8 @@ int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch
 int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap);
 /* development aid: microseconds per grid-wide barrier at the fused loop's launch shape (cooperative launch, 4 CTAs/SM) */
 double qe_debug_gridsync_us(qe_engine_t* e, int32_t iters);
+/* development aid: counters of the sorted loop's phase Q accumulated since the last reset (see qe_sorted.cuh) */
+int qe_debug_counters(qe_engine_t* e, uint64_t* out8_host, int32_t reset);
 const char* qe_build_info(void);
 
 #ifdef __cplusplus

@@ -62,6 +62,10 @@ ts = [buf[i] for i in range(m)]
 if m >= 4:
     for ph, name in enumerate(("A ", "B1", "B2")):
         print(f"phase {name} us:", " ".join(f"{(ts[1 + ph + 3 * k] - ts[ph + 3 * k]) / 1e3:.1f}" for k in range((m - 1) // 3)))
+cnt = (C.c_uint64 * 8)()
+if lib.qe_debug_counters(h, cnt, 1) == 0 and cnt[5]:
+    nw = cnt[5]
+    print(f'phase Q per warp-step: sweeps before resident {cnt[0]/nw:.2f}, us until resident mean {cnt[1]/nw/1e3:.1f} max {cnt[2]/1e3:.1f}, resident us mean {cnt[3]/nw/1e3:.1f} max {cnt[4]/1e3:.1f}, jobs at switch {cnt[6]/nw:.1f}, warp-steps {nw}')
 balg = 8 * A + 12
 print(f"grid={lib.qe_fused_grid_blocks(h)} best {N * K / best / 1e6:.3f} G agent-steps/s, alg {balg} B/agent-step -> {N * K * balg / best / 1e6:.1f} GB/s "
       f"({N * K * balg / best / 1e6 / 6549.4 * 100:.1f}% of measured HBM peak); episodes={int(ec.item())}")
