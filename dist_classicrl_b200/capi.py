@@ -73,6 +73,7 @@ SIGNATURES = {
     "qe_stream_u32": (u32, [u32, u32, u32, u32]),
     "qe_kernel_launches": (i64, [vp]),
     "qe_fused_grid_blocks": (i32, [vp]),
+    "qe_fused_form": (i32, [vp]),
     "qe_fused_phase_ns": (i32, [vp, vp, i32]),
     "qe_debug_gridsync_us": (C.c_double, [vp, i32]),
     "qe_debug_counters": (C.c_int, [vp, vp, i32]),

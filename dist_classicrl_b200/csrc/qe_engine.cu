@@ -52,7 +52,13 @@ struct qe_engine {
     uint32_t step = 0;       // global step counter (epoch / tag source)
     SortedScratch X{};       // scratch of the sorted fused loop (qe_sorted.cuh)
     int sorted_grid = 0;     // ghist was sized for this many blocks
-    int use_sorted = 1;      // fused loop: 1 = sort-based TD update (QE_SORTED=0 selects the writer-list kernel)
+    // The fused loop has two exact forms of the TD update: writer lists (qe_kernels.cuh; best while few agents share
+    // a row) and the per-step sort (qe_sorted.cuh; best once agents herd).  Both give identical results, so the engine
+    // times its launches and keeps using the faster form, trying the other one every kProbeEvery launches.
+    int strategy = 2;        // QE_SORTED env: 0 = writer lists only, 1 = sorted only, 2 (default) = pick by measurement
+    int current = 0, since_probe = 0, timed_kind = -1;
+    double timed_work = 0.0, rate[2] = {0.0, 0.0};  // agent-steps per millisecond of the last timed launch of each form
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     int last_grid = 0;
     std::mutex mu;
@@ -194,7 +200,9 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
         while (bits < 31 && (1ll << bits) < e->S) ++bits;
         e->X.passes = (bits + kRadixBits - 1) / kRadixBits;
     }
-    e->use_sorted = getenv("QE_SORTED") ? atoi(getenv("QE_SORTED")) : 1;
+    e->strategy = getenv("QE_SORTED") ? atoi(getenv("QE_SORTED")) : 2;
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
     e->T.spill_slots = 1024;
     CK(cudaMalloc(&e->T.spill, sizeof(uint32_t) * (size_t)e->T.spill_slots * kSpillCap));
     CK(cudaMalloc(&e->T.spill_next, 2 * sizeof(int)));
@@ -213,7 +221,9 @@ int qe_destroy(qe_engine_t* e) {
     cudaDeviceSynchronize();
     for (int b = 0; b < 2; ++b) { cudaFree(e->X.key[b]); cudaFree(e->X.val[b]); }
     cudaFree(e->X.rank); cudaFree(e->X.targ); cudaFree(e->X.mhist); cudaFree(e->X.rrec); cudaFree(e->X.rmask); cudaFree(e->X.hmask); cudaFree(e->X.hrec);
-    cudaFree(e->X.seg); cudaFree(e->X.rowtot); cudaFree(e->X.dbg); cudaFree(e->X.ghist);
+    cudaFree(e->X.seg); cudaFree(e->X.rowtot); cudaFree(e->X.dbg);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1); cudaFree(e->X.ghist);
     cudaFree(e->q_real); cudaFree(e->T.later_buf); cudaFree(e->T.spill); cudaFree(e->T.spill_next); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
     delete e;
@@ -225,6 +235,7 @@ float* qe_table_ptr(qe_engine_t* e) { return e->q_real; }
 int32_t qe_table_stride(qe_engine_t* e) { return e->ld; }
 int64_t qe_kernel_launches(qe_engine_t* e) { return e->launches; }
 int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
+int32_t qe_fused_form(qe_engine_t* e) { return e->current; }
 int qe_debug_counters(qe_engine_t* e, uint64_t* out8_host, int32_t reset) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (!e->X.dbg) return fail(QE_ERR_ARG, "no counters");
@@ -593,11 +604,35 @@ int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t
 
 // ---------------------------------------------------------------------------------------------- fused loop
 }  // extern "C"
+constexpr int kProbeEvery = 24;
+static int pick_form(qe_engine* e, const FusedArgs& F) {
+    if (e->timed_kind >= 0 && cudaEventQuery(e->ev1) == cudaSuccess) {  // the last timed launch has finished: book it
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess && ms > 0.0f) e->rate[e->timed_kind] = e->timed_work / ms;
+        e->timed_kind = -1;
+    }
+    (void)cudaGetLastError();
+    if (e->state_base != 0 || e->A > 32 || !e->X.seg) return 0;
+    if (e->strategy == 0 || e->strategy == 1) return e->strategy;
+    if (F.evaluate) return e->current;
+    if (e->rate[0] == 0.0) return 0;
+    if (e->rate[1] == 0.0) return 1;
+    const int best = e->rate[1] > e->rate[0] ? 1 : 0;
+    if (++e->since_probe >= kProbeEvery) {
+        e->since_probe = 0;
+        return best ^ 1;
+    }
+    return best;
+}
+
 template <int ENV, int LPR>
 static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     int blocks = 0;
     Table T = e->T;
-    if (e->use_sorted && e->state_base == 0) {
+    const int form = pick_form(e, F);
+    const bool timed = !F.evaluate && e->timed_kind < 0;
+    if (timed) CK(cudaEventRecord(e->ev0, st));
+    if (form == 1) {
         int rc = coop_blocks(e, fused_sorted_kernel<ENV, LPR>, (long long)F.n, &blocks);
         if (rc) return rc;
         if (blocks > kSortMaxBlocks * kSortStride) blocks = kSortMaxBlocks * kSortStride;
@@ -610,14 +645,18 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
         SortedScratch X = e->X;
         void* args[] = {&T, &F, &X};
         CK(cudaLaunchCooperativeKernel((void*)fused_sorted_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
-        e->launches++;
-        e->last_grid = blocks;
-        return QE_OK;
+    } else {
+        int rc = coop_blocks(e, fused_kernel<ENV, LPR>, (long long)F.n, &blocks);
+        if (rc) return rc;
+        void* args[] = {&T, &F};
+        CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
     }
-    int rc = coop_blocks(e, fused_kernel<ENV, LPR>, (long long)F.n, &blocks);
-    if (rc) return rc;
-    void* args[] = {&T, &F};
-    CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
+    if (timed) {
+        CK(cudaEventRecord(e->ev1, st));
+        e->timed_kind = form;
+        e->timed_work = (double)F.n * (double)F.steps;
+    }
+    e->current = form;
     e->launches++;
     e->last_grid = blocks;
     return QE_OK;

@@ -417,6 +417,18 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
                 my_h = __ldcg(X.hmask + gwarp + lane * nwarps);
                 my_r = __ldcg(X.rmask + gwarp + lane * nwarps);
             }
+            // the position every deferred reader of the first kRposTiles owned tiles polls, in shared memory (the part
+            // of the union the sort used): an unsuccessful poll then costs one round trip, not two
+            constexpr int kRposTiles = 8;
+            uint32_t* rpos = reinterpret_cast<uint32_t*>(s_union) + kValWords + (threadIdx.x >> 5);  // [tile][lane][warp]
+            const bool rpos_cached = in_regs && (kValWords + kRposTiles * 32 * 8 <= (kSortWords > kValWords ? kSortWords : kValWords));
+            if (rpos_cached) {
+                for (int t = 0; t < min(owned, kRposTiles); ++t) {
+                    const uint32_t dm = __shfl_sync(kFull, my_r, t);
+                    if ((dm >> lane) & 1u) rpos[(t * 32 + lane) * 8] = __ldcg(X.rrec + (size_t)((gwarp + t * nwarps) * 32 + lane) * 4);
+                }
+                __syncwarp();
+            }
             // A sequencer walks the segment of one row in agent order while targets are there.
             struct Seq {
                 int s, en, p, amx;
@@ -495,9 +507,10 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
             };
             // one visit of a swept sequencer job
             auto sequencer = [&](int p0) -> bool {
-                Seq q = seq_open(p0);
-                const uint64_t w = ld_relaxed_u64(X.targ + q.p);  // is the next target there at all?  (before the row is loaded)
-                if ((uint32_t)(w >> 38) != etag) return false;
+                const uint64_t w0 = ld_relaxed_u64(X.targ + p0);  // most segments are visited once: fetch their first target
+                Seq q = seq_open(p0);                              // together with the head record
+                const uint64_t w = q.p == p0 ? w0 : ld_relaxed_u64(X.targ + q.p);
+                if ((uint32_t)(w >> 38) != etag) return false;  // the next target is not there: nothing to do yet
                 seq_load_row(q);
                 const bool fin = seq_advance(q, w);
                 seq_store_row(q);
@@ -506,9 +519,12 @@ __global__ void __launch_bounds__(256, 4) fused_sorted_kernel(Table T, FusedArgs
             };
             // one deferred reader: the row max it waits for has been published -> deposit the target
             auto reader = [&](int i) -> bool {
-                const uint4 rec = __ldcg(reinterpret_cast<const uint4*>(X.rrec + (size_t)i * 4));
-                const uint64_t w = ld_relaxed_u64(X.mhist + rec.x);
+                const int t_own = (i / 32 - gwarp) / nwarps;  // which of this warp's tiles
+                const uint32_t mpos = (rpos_cached && t_own < kRposTiles) ? rpos[(t_own * 32 + (i & 31)) * 8]
+                                                                          : __ldcg(X.rrec + (size_t)i * 4);
+                const uint64_t w = ld_relaxed_u64(X.mhist + mpos);
                 if ((uint32_t)(w >> 32) != epoch) return false;
+                const uint4 rec = __ldcg(reinterpret_cast<const uint4*>(X.rrec + (size_t)i * 4));
                 const float tg = td_target_s(__uint_as_float(rec.z), __uint_as_float((uint32_t)w), F.gamma);
                 st_relaxed_u64(X.targ + rec.y, ((uint64_t)((etag << 6) | rec.w) << 32) | (uint64_t)__float_as_uint(tg));
                 return true;

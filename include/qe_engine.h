@@ -173,6 +173,9 @@ int qe_table_merge_dense(qe_engine_t* e, float* base_inout, const float* delta_s
 uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k);
 int64_t qe_kernel_launches(qe_engine_t* e);     /* kernels launched by this handle so far */
 int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch */
+/* form of the TD update the last fused launch used: 0 = writer lists, 1 = per-step sort (both exact; the engine times
+ * its launches and keeps the faster one; QE_SORTED=0/1 in the environment pins it) */
+int32_t qe_fused_form(qe_engine_t* e);
 /* phase clock of the last fused launch (synchronous): out_host[0] = %globaltimer (ns) at kernel start, then for each
  * of the first 10 vector steps the time after phase A (select + env step + writer registration), after phase B1 (TD
  * update, first pass) and after phase B2 (TD update, deferred agents).  Returns the number of values written. */
