@@ -56,7 +56,7 @@ struct qe_engine {
     // a row) and the per-step sort (qe_sorted.cuh; best once agents herd).  Both give identical results, so the engine
     // times its launches and keeps using the faster form, trying the other one every kProbeEvery launches.
     int strategy = 2;        // QE_SORTED env: 0 = writer lists only, 1 = sorted only, 2 (default) = pick by measurement
-    int current = 0, since_probe = 0, timed_kind = -1;
+    int current = 0, since_probe = 0, timed_kind = -1, n_timed[2] = {0, 0};
     double timed_work = 0.0, rate[2] = {0.0, 0.0};  // agent-steps per millisecond of the last timed launch of each form
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
@@ -604,21 +604,23 @@ int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t
 
 // ---------------------------------------------------------------------------------------------- fused loop
 }  // extern "C"
-constexpr int kProbeEvery = 24;
+constexpr int kProbeEvery = 12;
 static int pick_form(qe_engine* e, const FusedArgs& F) {
     if (e->timed_kind >= 0 && cudaEventQuery(e->ev1) == cudaSuccess) {  // the last timed launch has finished: book it
         float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess && ms > 0.0f) e->rate[e->timed_kind] = e->timed_work / ms;
+        // (the first launch of a form pays for module loading and cold caches: it is not a measurement)
+        if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess && ms > 0.0f && ++e->n_timed[e->timed_kind] >= 2)
+            e->rate[e->timed_kind] = e->timed_work / ms;
         e->timed_kind = -1;
     }
     (void)cudaGetLastError();
     if (e->state_base != 0 || e->A > 32 || !e->X.seg) return 0;
     if (e->strategy == 0 || e->strategy == 1) return e->strategy;
     if (F.evaluate) return e->current;
-    if (e->rate[0] == 0.0) return 0;
-    if (e->rate[1] == 0.0) return 1;
+    if (e->n_timed[0] < 2) return 0;
+    if (e->n_timed[1] < 2) return 1;
     const int best = e->rate[1] > e->rate[0] ? 1 : 0;
-    if (++e->since_probe >= kProbeEvery) {
+    if (++e->since_probe >= kProbeEvery) {  // the workload drifts (agents herd as the table is learned): look again
         e->since_probe = 0;
         return best ^ 1;
     }

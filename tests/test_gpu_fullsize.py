@@ -150,3 +150,24 @@ def test_config3_chunking_and_determinism(capi):
     finally:
         for x in (a, b, c):
             x.close()
+
+
+@pytest.mark.parametrize("form", ["0", "1"])
+@pytest.mark.parametrize("S,A,N,steps", [(2000, 16, 50_000, 24), (97, 5, 4096, 16), (300_000, 8, 200_000, 10)])
+def test_both_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form, S, A, N, steps):
+    """QE_SORTED pins the form of the TD update (0 = writer lists, 1 = per-step sort); both must reproduce the
+    oracle bit for bit, also when hundreds of agents herd on one row."""
+    monkeypatch.setenv("QE_SORTED", form)
+    seed = 9
+    q_o, st_o, rew_o, _ = _oracle(S, A, N, steps, seed, 1)
+    assert np.bincount(st_o, minlength=S).max() > (40 if N > 10 * S else 1)
+    r = Run(capi, S, A, N, seed, 1)
+    try:
+        r.steps(steps // 2)
+        r.steps(steps - steps // 2)
+        assert capi.lib().qe_fused_form(r.h) == int(form)
+        assert np.array_equal(r.states.cpu().numpy(), st_o)
+        assert np.array_equal(r.ep.cpu().numpy(), rew_o)
+        assert np.array_equal(r.table(), q_o)
+    finally:
+        r.close()
