@@ -60,7 +60,8 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread about every millisecond
+    (the timed region of the default run is ~10 ms long, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -69,8 +70,34 @@ class ClockSampler:
         self.rows: list[list[str]] = []
         self.proc = None
         self.idx = gpu_index
+        self.nvml = None
+        self.samples: list[tuple[int, int]] = []  # (sm MHz, reasons bit mask)
+        self.smax = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                pass
+        return self.idx
 
     def start(self) -> None:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -78,11 +105,35 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self) -> None:
+        pynvml, h = self.nvml
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append((int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(reasons_fn(h))))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.0005)
+
     def _read(self) -> None:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            pynvml = self.nvml[0]
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            sm = [float(c) for c, _ in self.samples]
+            reasons = sorted({name for _, r in self.samples for name, b in bits.items() if r & b})
+            busy = [x for x in sm if self.smax and x > 0.5 * self.smax] or sm
+            try:
+                pynvml.nvmlShutdown()
+            except Exception:  # noqa: BLE001
+                pass
+            return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -99,7 +150,7 @@ class ClockSampler:
                 continue
         busy = [x for x in sm if smax and x > 0.5 * smax] or sm
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------- reference / CPU arm
@@ -359,11 +410,11 @@ def run_ours(args) -> dict | None:
         _, _, _, sd = runner.run_steps(1, env, sd)  # returns host copies of the agents' running returns
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    h2d = n * slots * 4 + 12
-    d2h = n * 4 + 16 + 4
+    h2d = n * slots * 4 + n * 4 + 12  # the step's uniforms + the agents' running returns (state dict) + eps/lr of the step
+    d2h = n * 4 + 16                  # the running returns + {sum, count} of the episodes that finished in the step
     e2e = {"value": world * n * Ke / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
            "steps": Ke, "api": ("ReplicatedQLearning(sync_every=1)." if tp is not None else "SingleThreadQLearning.") +
-           "run_steps(1, env, state_dict) with PredrawnUniforms in pinned host memory; host copy of the running returns every step"}
+           "run_steps(1, env, state_dict): the step's pre-drawn uniforms (PredrawnUniforms, pinned host memory) and the state dict's running returns go host->device, the returns and the episode statistics come back, every step"}
     del algo, env, runner, rt
 
     # ---------------- sharded 100M-state table (config 4), bounded

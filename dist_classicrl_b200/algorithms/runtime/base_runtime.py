@@ -21,13 +21,14 @@ from typing import Any
 
 import numpy as np
 
-from dist_classicrl_b200 import capi
+from dist_classicrl_b200 import capi, hostmem
 from dist_classicrl_b200.environments.custom_env import DeviceVecEnv
 from dist_classicrl_b200.rng import PredrawnUniforms, explore_threshold, is_engine_rng
 
 logger = logging.getLogger(__name__)
 
 _TRACE_BYTES = 256 << 20  # per-chunk budget of the episode-return trace
+_PIN_BYTES = 64 << 10  # host arrays at least this large are page-locked in place before they are copied
 
 
 def _split(states):
@@ -234,18 +235,29 @@ class BaseRuntime(ABC):
         algo._before_device_op()
         n = env.num_envs
         dev = env.device
-        ep_ret = agent_rewards if isinstance(agent_rewards, torch.Tensor) else torch.from_numpy(
-            np.ascontiguousarray(agent_rewards, dtype=np.float32)).to(dev)
+        # the caller's running returns (a plain NumPy array in the reference's state dictionary, STR:57) are page-locked
+        # in place on first sight: the per-call upload and the copy back are then asynchronous DMA on this stream
+        host_ret = None
+        if isinstance(agent_rewards, torch.Tensor):
+            ep_ret = agent_rewards
+        else:
+            if (isinstance(agent_rewards, np.ndarray) and agent_rewards.dtype == np.float32 and agent_rewards.shape == (n,)
+                    and agent_rewards.nbytes >= _PIN_BYTES and hostmem.pin(agent_rewards)):
+                host_ret = torch.from_numpy(agent_rewards)
+                ep_ret = torch.empty(n, dtype=torch.float32, device=dev)
+                ep_ret.copy_(host_ret, non_blocking=True)
+            else:
+                ep_ret = torch.from_numpy(np.ascontiguousarray(agent_rewards, dtype=np.float32)).to(dev)
         variant = algo._variant(n, False, env.dict_obs)
         full = self.history_mode == "full"
         chunk = max(1, min(steps, _TRACE_BYTES // (4 * n))) if full else steps
-        ep_sum = torch.zeros(1, dtype=torch.float64, device=dev)
-        ep_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        ep_stats = torch.zeros(2, dtype=torch.int64, device=dev)  # [0] = float64 sum of finished episodes, [1] = their count
         history: list[float] = []
         predrawn = isinstance(algo._rng, PredrawnUniforms)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         ag = env.agents_struct(ep_ret)
         done = 0
+        stats_host = torch.zeros(2, dtype=torch.int64)
         while done < steps:
             k = min(chunk, steps - done)
             th = np.empty(k, dtype=np.uint64)
@@ -296,8 +308,14 @@ class BaseRuntime(ABC):
                     buf = torch.empty((k, n), dtype=dt, device=dev)
                     setattr(run, field, buf.data_ptr())
                     keep.append((name, buf))
-            run.episode_sum, run.episode_count = ep_sum.data_ptr(), ep_cnt.data_ptr()
+            run.episode_sum, run.episode_count = ep_stats.data_ptr(), ep_stats.data_ptr() + 8
             capi.check(lib.qe_fused_steps(algo.handle, C.byref(ag), C.byref(run), stream))
+            done += k
+            if done == steps:  # the results travel back behind the last launch, before the one synchronisation
+                stats_host = self._stats_host()
+                stats_host.copy_(ep_stats, non_blocking=True)
+                if host_ret is not None:
+                    host_ret.copy_(ep_ret, non_blocking=True)
             capi.check(lib.qe_sync(algo.handle, stream))
             if full:
                 flat = tr_ep.reshape(-1)
@@ -307,12 +325,20 @@ class BaseRuntime(ABC):
                     trace.setdefault("episode_rows", []).extend(row[~np.isnan(row)].tolist() for row in host)
             for name, buf in keep:
                 trace.setdefault(name, []).append(buf.cpu().numpy())
-            done += k
         if not evaluate:
             algo._device_wrote()
         env.refresh_after_fused()
-        self.last_episode_count = int(ep_cnt.item())
-        self.last_episode_sum = float(ep_sum.item())
-        if isinstance(agent_rewards, np.ndarray):
+        self.last_episode_count = int(stats_host[1])
+        self.last_episode_sum = float(stats_host[:1].view(torch.float64)[0])
+        if host_ret is None and isinstance(agent_rewards, np.ndarray):
             agent_rewards[:] = ep_ret.cpu().numpy()
         return history
+
+    def _stats_host(self):
+        """Page-locked landing buffer of the fused loop's episode statistics."""
+        import torch
+
+        buf = getattr(self, "_stats_pinned", None)
+        if buf is None:
+            buf = self._stats_pinned = torch.zeros(2, dtype=torch.int64).pin_memory()
+        return buf

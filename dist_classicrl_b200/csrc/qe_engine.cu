@@ -292,6 +292,24 @@ int qe_table_fill_random(qe_engine_t* e, uint32_t seed, void* stream) {
     CK(cudaGetLastError());
     return QE_OK;
 }
+// Page-lock a caller-owned host array in place, so that the *_host copies and the runtimes' per-step transfers of
+// it are asynchronous DMA.  1 = newly registered (pair with qe_host_unregister), 0 = was page-locked already.
+int qe_host_register(void* host, uint64_t bytes) {
+    if (host == nullptr || bytes == 0) return fail(QE_ERR_ARG, "qe_host_register: empty range");
+    cudaError_t rc = cudaHostRegister(host, (size_t)bytes, cudaHostRegisterDefault);
+    if (rc == cudaSuccess) return 1;
+    cudaGetLastError();  // not sticky: leave no stale error behind for the next launch check
+    if (rc == cudaErrorHostMemoryAlreadyRegistered) return 0;
+    return fail(QE_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(rc));
+}
+int qe_host_unregister(void* host) {
+    cudaError_t rc = cudaHostUnregister(host);
+    if (rc != cudaSuccess) {
+        cudaGetLastError();
+        return fail(QE_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(rc));
+    }
+    return QE_OK;
+}
 int qe_sync(qe_engine_t* e, void* stream) {
     std::lock_guard<std::mutex> lk(e->mu);
     return check_device_errors(e, (cudaStream_t)stream);

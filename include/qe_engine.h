@@ -59,6 +59,11 @@ int qe_table_fill(qe_engine_t* e, float value, void* stream);
 /* throughput runs: table[s][a] = (stream hash >> 8) * 2^-24, uniform in [0,1) */
 int qe_table_fill_random(qe_engine_t* e, uint32_t seed, void* stream);
 int qe_sync(qe_engine_t* e, void* stream); /* cudaStreamSynchronize + raise deferred device errors */
+/* Page-lock a caller-owned host array in place (the reference's state dictionaries hold plain NumPy arrays the trainer
+ * updates in place, STR:57, 70-75; page-locked, their per-step copies are asynchronous DMA).  Returns 1 if the range
+ * was registered by this call (pair with qe_host_unregister), 0 if it already was page-locked, < 0 on error. */
+int qe_host_register(void* host, uint64_t bytes);
+int qe_host_unregister(void* host);
 
 /* ---- select: replaces choose_actions and its 8 variants (QLO:263-726) ------------------------------------
  * mask_bits[N]: bit a set = action a legal (A <= 32), NULL = no masks.  mask_bytes[N][A] (uint8 truthy) is the

@@ -219,3 +219,104 @@ def test_train_entry_point_with_validation(api):
     assert set(sd) == {"states", "infos", "rewards", "episode_rewards"}
     with pytest.raises(AssertionError):
         rt.train(env, steps=10, val_env=val_env, val_every_n_steps=10)
+
+
+def test_state_dict_returns_are_pinned_in_place_and_match_the_oracle(api):
+    """A state dictionary's running returns (plain NumPy, STR:57) large enough to be page-locked in place: the array
+    object is updated in place across resumed ``run_steps`` calls and equals the oracle's accumulator; the episode
+    statistics of summary mode equal the oracle's too."""
+    import math
+
+    from dist_classicrl_b200 import hostmem
+    from oracle import c_oracle as co
+    from oracle import rng as orng
+
+    s, a, n, calls, k = 5000, 16, 32768, 4, 3
+    u = orng.draw_uniforms(3, 0, calls * k, n, 4)
+    u0 = orng.draw_uniforms(3, 0xFFFFFFFF, 1, n, 4)[0]
+    env = api.env.HashMDPVecEnv(n, s, a, env_seed=7, p_term=0.05)
+    algo = api.QL(s, a, 0.9, seed=0)
+    env.attach(algo)
+    env.reset_with(u0)
+    algo._rng = env._rng = api.rng.PredrawnUniforms(u)
+    rt = api.rt.SingleThreadQLearning(algo, api.sch.ConstantSchedule(0.25), api.sch.ConstantSchedule(0.2))
+    rt.history_mode = "summary"
+    rewards = np.zeros(n, dtype=np.float32)
+    sd = {"states": None, "infos": {}, "rewards": rewards}
+    ep_sum, ep_cnt = 0.0, 0
+    for _ in range(calls):
+        _mean, _hist, _env, sd = rt.run_steps(k, env, sd)
+        assert sd["rewards"] is rewards
+        ep_sum += rt.last_episode_sum
+        ep_cnt += rt.last_episode_count
+    assert hostmem._registered.get(rewards.ctypes.data) == rewards.nbytes
+    assert torch.from_numpy(rewards).is_pinned()
+    # oracle on the same streams
+    states, masks = co.mdp_reset(u0, s, a, 7)
+    q = np.zeros((s, a), dtype=np.float32)
+    res = co.run(co.ENV_MDP, q, None, states, masks, num_states=s, env_seed=7, term_thresh=int(math.ceil(0.05 * 2.0**32)),
+                 uniforms=u, steps=calls * k, eps_thresh=np.full(calls * k, orng.explore_threshold(0.2), dtype=np.uint64),
+                 lr=np.full(calls * k, 0.25, dtype=np.float32), gamma=0.9, empty_all=True)
+    assert res["rc"] == 0
+    np.testing.assert_array_equal(rewards, res["agent_rewards"])
+    np.testing.assert_array_equal(algo.q_table, q)
+    assert ep_cnt == res["ep_count"] and abs(ep_sum - res["ep_sum"]) <= 1e-6 * max(1.0, abs(res["ep_sum"]))
+    ptr = rewards.ctypes.data
+    del rewards, sd
+    import gc
+
+    gc.collect()
+    assert ptr not in hostmem._registered
+
+
+def _async_rank(api, msg, algo, steps, episode_len, val_every, val_steps, batch, out):
+    from dist_classicrl_b200.environments.rigged_two_armed_bandit import make_bandit_vec_env
+
+    rt = api.rt.DistAsyncQLearning(algo, api.sch.ConstantSchedule(1.0), api.sch.LinearSchedule(1.0, 1.0), messenger=msg)
+    out[msg.rank] = (rt, rt.train(env=make_bandit_vec_env(1, episode_len), steps=steps, val_env=make_bandit_vec_env(1, episode_len),
+                                  val_every_n_steps=val_every, val_steps=val_steps, val_episodes=None, curr_state_dict={}, batch_size=batch))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dist_async_train_skips_validation_and_updates_q_table(api, world):  # T-MPI:100-147 (ranks as threads)
+    import threading
+
+    from dist_classicrl_b200.algorithms.runtime.q_learning_async_dist import ThreadMessenger
+
+    algos = []
+    for _ in range(world):
+        algo = api.QL(state_size=1, action_size=2, discount_factor=1.0, seed=0)
+        algo._rng = DeterministicRNG()
+        algos.append(algo)
+    out = {}
+    ts = [threading.Thread(target=_async_rank, args=(api, m, a, 5, 6, 6, 6, 8, out)) for m, a in zip(ThreadMessenger.group(world), algos)]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    assert len(out) == world
+    rt, (hist, val, envs, state) = out[0]
+    assert val == [] and isinstance(hist, list) and envs is None and state is None
+    assert rt.algorithm.q_table.shape == (1, 2) and rt.algorithm.q_table[0, 1] == 5.0
+    assert rt.lr_schedule.get_value() == 1.0 and rt.exploration_rate_schedule.get_value() == 6.0
+    for r in range(1, world):
+        _rt, (hist, val, env, state) = out[r]
+        assert hist == [] and val == [] and env is not None and "states" in state
+
+
+def test_dist_async_train_with_validation(api):  # T-MPI:150-205
+    import threading
+
+    from dist_classicrl_b200.algorithms.runtime.q_learning_async_dist import ThreadMessenger
+
+    out = {}
+    algos = []
+    for _ in range(2):
+        algo = api.QL(state_size=1, action_size=2, discount_factor=1.0, seed=0)
+        algo._rng = DeterministicRNG()
+        algos.append(algo)
+    ts = [threading.Thread(target=_async_rank, args=(api, m, a, 6, 5, 3, 5, 2, out)) for m, a in zip(ThreadMessenger.group(2), algos)]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    rt, (hist, val, _envs, _state) = out[0]
+    assert len(val) == 2 and all(v == 5.0 for v in val)
+    assert [float(h) for h in hist] == [5.0]
+    assert rt.exploration_rate_schedule.get_value() == 7.0
