@@ -150,9 +150,11 @@ class DistAsyncQLearning(BaseRuntime):
         have = 0
         steps_since_val = 0
         step = 0
-        while running:
+        while running or have:
+            # one batch per turn: up to batch_size transitions, cut short at the validation boundary, by an empty queue
+            # (MPI:103-108) or by the sentinel
             want = min(self.batch_size, val_every_n_steps - steps_since_val)
-            while have < want:
+            while running and have < want:
                 try:
                     rec = self.experience_queue.get(timeout=0.1)
                 except queue.Empty:
@@ -162,22 +164,10 @@ class DistAsyncQLearning(BaseRuntime):
                     break
                 pending.append(rec)
                 have += len(rec[0])
-            if not running:
-                want = have  # drain what is left (in batches, below)
-            while have and (have >= want or not running) and steps_since_val < val_every_n_steps:
-                take = min(have, self.batch_size, val_every_n_steps - steps_since_val)
+            take = min(have, want)
+            if take:
                 batch, pending = _take(pending, take)
                 have -= take
-                self._learn_batch(batch)
-                steps_since_val += take
-                step += take
-                if steps_since_val >= val_every_n_steps:
-                    break
-                want = min(self.batch_size, val_every_n_steps - steps_since_val)
-            if steps_since_val < val_every_n_steps and have and have < want and running:
-                # the queue ran dry before the batch filled up: learn what is there (MPI:105-108 breaks on queue.Empty)
-                batch, pending = _take(pending, have)
-                take, have = have, 0
                 self._learn_batch(batch)
                 steps_since_val += take
                 step += take

@@ -96,6 +96,17 @@ def test_batches_follow_queue_order_and_size():
     assert len(hist) >= 4 and set(hist) == {4.0}
 
 
+def test_nothing_queued_is_dropped_when_the_sentinel_arrives_early():
+    """Validation every 5 transitions while 32 are queued in 8 records of 4: every transition is learned, 6 validations."""
+    out = {}
+    ms = AD.ThreadMessenger.group(2)
+    ts = [threading.Thread(target=_run_rank, args=(m, 8, 4, 5, 4, 3, 4, out)) for m in ms]
+    [t.start() for t in ts]
+    [t.join(timeout=60) for t in ts]
+    (_hist, val, _e, _s), _q, eps, _lr, batches = out[0]
+    assert sum(batches) == 32 and max(batches) <= 3 and len(val) == 6 and eps == 33.0
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
