@@ -49,6 +49,8 @@ SIGNATURES = {
     "qe_table_fill": (C.c_int, [vp, f32, vp]),
     "qe_table_fill_random": (C.c_int, [vp, u32, vp]),
     "qe_sync": (C.c_int, [vp, vp]),
+    "qe_radix_encode": (C.c_int, [vp, vp, i32, vp, i64, vp]),
+    "qe_radix_decode": (C.c_int, [vp, vp, vp, i32, vp, i64, vp]),
     "qe_host_register": (C.c_int, [vp, u64]),
     "qe_host_unregister": (C.c_int, [vp]),
     "qe_select": (C.c_int, [vp, vp, vp, vp, vp, i32, u32, u32, u32, u64, i32, i32, vp, i32, vp]),

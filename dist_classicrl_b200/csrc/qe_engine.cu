@@ -11,6 +11,7 @@
 #include "../../include/qe_engine.h"
 #include "qe_kernels.cuh"
 #include "qe_sorted.cuh"
+#include "qe_radix.cuh"
 
 using namespace qe;
 
@@ -292,6 +293,47 @@ int qe_table_fill_random(qe_engine_t* e, uint32_t seed, void* stream) {
     CK(cudaGetLastError());
     return QE_OK;
 }
+// ---------------------------------------------------------------------------------------------- flatten wrappers
+static int radix_spec(RadixSpec& R, const int64_t* nvec_host, const int64_t* radix_host, int dims) {
+    if (dims <= 0 || dims > kRadixMaxDims) return fail(QE_ERR_ARG, "radix: 1 <= dims <= %d", kRadixMaxDims);
+    if (radix_host == nullptr) return fail(QE_ERR_ARG, "radix: radix_host is NULL");
+    R.dims = dims;
+    for (int d = 0; d < kRadixMaxDims; ++d) {
+        R.radix[d] = d < dims ? (long long)radix_host[d] : 1;
+        R.nvec[d] = (d < dims && nvec_host) ? (long long)nvec_host[d] : 1;
+    }
+    return QE_OK;
+}
+static int radix_grid(int64_t n) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (n + 255) / 256;
+    return (int)std::min<int64_t>(tiles, (int64_t)sms * 8);
+}
+int qe_radix_encode(const int32_t* vectors, const int64_t* radix_host, int32_t dims, int64_t* out, int64_t n, void* stream) {
+    RadixSpec R;
+    int rc = radix_spec(R, nullptr, radix_host, dims);
+    if (rc) return rc;
+    if (n <= 0) return QE_OK;
+    radix_encode_kernel<<<radix_grid(n), 256, 256 * (dims | 1) * sizeof(int32_t), (cudaStream_t)stream>>>(vectors, R, (long long*)out, (long long)n);
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+int qe_radix_decode(const int64_t* indices, const int64_t* nvec_host, const int64_t* radix_host, int32_t dims, int32_t* out, int64_t n,
+                    void* stream) {
+    RadixSpec R;
+    if (nvec_host == nullptr) return fail(QE_ERR_ARG, "radix: nvec_host is NULL");
+    int rc = radix_spec(R, nvec_host, radix_host, dims);
+    if (rc) return rc;
+    for (int d = 0; d < dims; ++d)
+        if (R.radix[d] == 0 || R.nvec[d] == 0) return fail(QE_ERR_ARG, "radix: zero radix / nvec entry");
+    if (n <= 0) return QE_OK;
+    radix_decode_kernel<<<radix_grid(n), 256, 256 * (dims | 1) * sizeof(int32_t), (cudaStream_t)stream>>>((const long long*)indices, R, out, (long long)n);
+    CK(cudaGetLastError());
+    return QE_OK;
+}
+
 // Page-lock a caller-owned host array in place, so that the *_host copies and the runtimes' per-step transfers of
 // it are asynchronous DMA.  1 = newly registered (pair with qe_host_unregister), 0 = was page-locked already.
 int qe_host_register(void* host, uint64_t bytes) {

@@ -59,6 +59,16 @@ int qe_table_fill(qe_engine_t* e, float value, void* stream);
 /* throughput runs: table[s][a] = (stream hash >> 8) * 2^-24, uniform in [0,1) */
 int qe_table_fill_random(qe_engine_t* e, uint32_t seed, void* stream);
 int qe_sync(qe_engine_t* e, void* stream); /* cudaStreamSynchronize + raise deferred device errors */
+/* ---- flatten wrappers: batched mixed-radix encode / decode of MultiDiscrete vectors ------------------------------
+ * Replaces utils.encode_multi_discretes (utils.py:51-69: out[i] = sum_d vectors[i][d] * radix[d]) and
+ * utils.decode_to_multi_discretes (utils.py:95-115: out[i][d] = (indices[i] // radix[d]) % nvec[d]) behind
+ * FlattenMultiDiscreteObservationsWrapper.observation / FlattenMultiDiscreteActionsWrapper.action
+ * (wrappers/flatten_multidiscrete_wrapper.py:139-161, 61-76).  vectors / indices / out are DEVICE arrays
+ * ([n][dims] int32 row-major, [n] int64); radix_host = compute_radix(nvec) and nvec_host are HOST arrays of `dims`
+ * (<= 32) entries, passed to the kernel by value.  Asynchronous on `stream`. */
+int qe_radix_encode(const int32_t* vectors, const int64_t* radix_host, int32_t dims, int64_t* out, int64_t n, void* stream);
+int qe_radix_decode(const int64_t* indices, const int64_t* nvec_host, const int64_t* radix_host, int32_t dims, int32_t* out, int64_t n,
+                    void* stream);
 /* Page-lock a caller-owned host array in place (the reference's state dictionaries hold plain NumPy arrays the trainer
  * updates in place, STR:57, 70-75; page-locked, their per-step copies are asynchronous DMA).  Returns 1 if the range
  * was registered by this call (pair with qe_host_unregister), 0 if it already was page-locked, < 0 on error. */
