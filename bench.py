@@ -309,6 +309,8 @@ def run_ours(args) -> dict | None:
     rep = D.ReplicatedQLearning(rt0, tp, sync_every=SYNC_EVERY) if tp is not None else None
     t_next = [0]
 
+    learn_mode = [capi.QE_LEARN_SEQUENTIAL]
+
     def launch(k):
         th = np.full(k, explore_threshold(EPS), dtype=np.uint64)
         lrs = np.full(k, LR, dtype=np.float32)
@@ -322,6 +324,7 @@ def run_ours(args) -> dict | None:
         run.agent0 = env.agent0
         run.use_masks = 1
         run.empty_all = int(a > 10)
+        run.learn_mode = learn_mode[0]
         run.episode_sum, run.episode_count = stats.data_ptr(), ep_cnt.data_ptr()
         capi.check(lib.qe_fused_steps(algo.handle, C.byref(ag), C.byref(run), C.c_void_p(stream.cuda_stream)))
         t_next[0] += k
@@ -389,6 +392,42 @@ def run_ours(args) -> dict | None:
         late = {"td_update_form": ["writer lists", "per-step sort"][int(lib.qe_fused_form(algo.handle))], "after_vector_steps": 256, "steps": 4 * SYNC_EVERY, "ms_per_step": late_ms, "value": n / (late_ms * 1e-3), "unit": "agent-steps/s"}
     episodes = int(sum_over_ranks(float(ep_cnt.item())))
     del algo, env, rep, rt0
+
+    # ---------------- the same loop with the plain-atomics update (learn_vec, QLO:819-891) instead of the exact sequential
+    # one: what the ordering guarantee costs on this workload (BASELINE north_star, item 3).  Not the headline: the
+    # reference's trainers call learn(), which is sequential.
+    atomics = None
+    if world == 1 and not args.no_late:
+        algo, env = make()
+        ep_ret = torch.zeros(n, dtype=torch.float32, device=dev)
+        ag = env.agents_struct(ep_ret)
+        stats.zero_()
+        ep_cnt.zero_()
+        t_next[0] = 0
+        learn_mode[0] = capi.QE_LEARN_ACCUMULATE
+        for k in chunks(W):
+            launch(k)
+        capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for k in chunks(K):
+            launch(k)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
+        learn_mode[0] = capi.QE_LEARN_SEQUENTIAL
+        acc_ms = a0.elapsed_time(a1) / K
+        m = lib.qe_fused_phase_ns(algo.handle, buf, 33)
+        acc_phases = None
+        if m >= 4:
+            ks = (m - 1) // 3
+            acc_phases = {name: sum(buf[1 + ph + 3 * j] - buf[ph + 3 * j] for j in range(ks)) / ks / 1e3
+                          for ph, name in enumerate(("select_step_us", "bootstrap_delta_us", "atomic_scatter_us"))}
+        peak_gbs = measured_peak()[0]
+        atomics = {"td_update": "learn_vec semantics: snapshot bootstrap + atomicAdd scatter (not what the reference's trainers call)",
+                   "value": n / (acc_ms * 1e-3), "unit": "agent-steps/s", "steps": K, "ms_per_step": acc_ms, "phase_us_per_step": acc_phases,
+                   "roofline_frac": n * alg_bytes(a) / (acc_ms * 1e-3) / 1e9 / peak_gbs, "kernel": "fused_kernel<MDP,2,ACC>" if workload != "c2" else "fused_kernel<TTT,2,ACC>"}
+        del algo, env
 
     # ---------------- e2e through the public API: per step H2D of that step's uniforms (pinned) + D2H of the results
     algo, env = make()
@@ -486,6 +525,8 @@ def run_ours(args) -> dict | None:
         "data": "synthetic", "config": cfg, "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
         "episodes": episodes,
     }
+    if atomics is not None:
+        out["atomics_mode"] = atomics
     if cpu_baseline is not None:
         out["cpu_baseline"] = cpu_baseline
     if sharded is not None:

@@ -56,6 +56,9 @@ class BaseRuntime(ABC):
         self.history_mode = "full"  # "summary": keep only count/sum of finished episodes (huge agent counts)
         self.last_episode_count = 0
         self.last_episode_sum = 0.0
+        # "sequential": the reference trainers' update, learn -> learn_iter (BRT:245-259, QLO:893-934).  "accumulate":
+        # learn_vec instead (QLO:819-891; snapshot bootstrap + accumulating scatter = plain atomics on the GPU)
+        self.td_update = "sequential"
 
     @abstractmethod
     def init_training(self) -> None:
@@ -107,10 +110,11 @@ class BaseRuntime(ABC):
         next_obs, next_masks = _split(next_states)
         assert isinstance(states, dict) == isinstance(next_states, dict)
         lr = self.lr_schedule.get_value()
+        learn = self.algorithm.learn_vec if self.td_update == "accumulate" else self.algorithm.learn
         if next_masks is None:
-            self.algorithm.learn(obs, actions, rewards, next_obs, terminateds, lr)
+            learn(obs, actions, rewards, next_obs, terminateds, lr)
         else:
-            self.algorithm.learn(obs, actions, rewards, next_obs, terminateds, lr, next_masks)
+            learn(obs, actions, rewards, next_obs, terminateds, lr, next_masks)
         n_updates = len(obs)
         self.lr_schedule.update(n_updates)
         self.exploration_rate_schedule.update(n_updates)
@@ -273,6 +277,7 @@ class BaseRuntime(ABC):
             run = capi.QeRun()
             run.steps = k
             run.evaluate = int(evaluate)
+            run.learn_mode = capi.QE_LEARN_ACCUMULATE if self.td_update == "accumulate" else capi.QE_LEARN_SEQUENTIAL
             run.explore_thresholds_host = th.ctypes.data_as(C.c_void_p)
             run.learning_rates_host = lrs.ctypes.data_as(C.c_void_p)
             u_dev = None

@@ -32,7 +32,7 @@ class QeRun(C.Structure):
         ("stream_seed", u32), ("t0", u32), ("agent0", u32), ("env_stream_seed", u32), ("env_t0", u32),
         ("empty_all", i32), ("use_masks", i32),
         ("trace_actions", vp), ("trace_rewards", vp), ("trace_terminated", vp), ("trace_next_states", vp),
-        ("trace_episode_returns", vp), ("episode_sum", vp), ("episode_count", vp), ("evaluate", i32),
+        ("trace_episode_returns", vp), ("episode_sum", vp), ("episode_count", vp), ("evaluate", i32), ("learn_mode", i32),
     ]
 
 

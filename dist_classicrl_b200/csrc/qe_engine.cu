@@ -675,6 +675,7 @@ static int pick_form(qe_engine* e, const FusedArgs& F) {
     }
     (void)cudaGetLastError();
     if (e->state_base != 0 || e->A > 32 || !e->X.seg) return 0;
+    if (F.accumulate) return 0;  // the plain-atomics update lives in fused_kernel
     if (e->strategy == 0 || e->strategy == 1) return e->strategy;
     if (F.evaluate) return e->current;
     if (e->n_timed[0] < 2) return 0;
@@ -692,7 +693,7 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     int blocks = 0;
     Table T = e->T;
     const int form = pick_form(e, F);
-    const bool timed = !F.evaluate && e->timed_kind < 0;
+    const bool timed = !F.evaluate && !F.accumulate && e->timed_kind < 0;
     if (timed) CK(cudaEventRecord(e->ev0, st));
     if (form == 1) {
         int rc = coop_blocks(e, fused_sorted_kernel<ENV, LPR>, (long long)F.n, &blocks);
@@ -707,6 +708,11 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
         SortedScratch X = e->X;
         void* args[] = {&T, &F, &X};
         CK(cudaLaunchCooperativeKernel((void*)fused_sorted_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
+    } else if (F.accumulate) {
+        int rc = coop_blocks(e, fused_kernel<ENV, LPR, true>, (long long)F.n, &blocks);
+        if (rc) return rc;
+        void* args[] = {&T, &F};
+        CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPR, true>, dim3(blocks), dim3(256), args, 0, st));
     } else {
         int rc = coop_blocks(e, fused_kernel<ENV, LPR>, (long long)F.n, &blocks);
         if (rc) return rc;
@@ -778,6 +784,8 @@ int qe_fused_steps(qe_engine_t* e, const qe_agents_t* ag, const qe_run_t* run, v
     F.ep_sum = run->episode_sum; F.ep_count = run->episode_count;
     F.phase_ns = e->phase_ns;
     F.evaluate = run->evaluate != 0;
+    F.accumulate = run->learn_mode == QE_LEARN_ACCUMULATE;
+    if (run->learn_mode != QE_LEARN_SEQUENTIAL && run->learn_mode != QE_LEARN_ACCUMULATE) return fail(QE_ERR_ARG, "unknown learn_mode %d", run->learn_mode);
     e->phase_steps = run->steps < 10 ? run->steps : 10;
     if ((F.ep_sum == nullptr) != (F.ep_count == nullptr)) return fail(QE_ERR_ARG, "episode_sum and episode_count go together");
     if (!F.evaluate) e->step += (uint32_t)run->steps;

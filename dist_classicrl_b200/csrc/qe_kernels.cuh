@@ -1133,6 +1133,7 @@ struct FusedArgs {
     double* ep_sum;
     unsigned long long* ep_count;
     int evaluate;                // 1: no TD update (evaluation loops, BRT:293-384): select + env step only
+    int accumulate;              // 1: learn_vec semantics (QLO:819-891): bootstrap from the table as it was before the step, atomicAdd scatter
     uint64_t* phase_ns;          // optional [31]: %globaltimer at launch and after each of the 3 phases of the first 10 steps
 };
 
@@ -1143,7 +1144,7 @@ __device__ __forceinline__ uint32_t env_mask(int s, uint32_t envw, int A, uint32
     return A >= 32 ? 0xFFFFFFFFu : ((1u << A) - 1u);
 }
 
-template <int ENV, int LPR>
+template <int ENV, int LPR, bool ACC = false>  // ACC: the plain-atomics (learn_vec) update instead of the exact sequential one
 __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T, FusedArgs F) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double s_sum[8];
@@ -1180,7 +1181,7 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
                 s = cur[i];
                 // register as a writer of row s right away: the ticket travels while the row is fetched
                 info = reinterpret_cast<unsigned long long*>(row_info(T, s));
-                if (!F.evaluate) {
+                if (!F.evaluate && !ACC) {
                     atomicMax(info, (unsigned long long)epoch << 32);  // a stale (older-epoch) counter restarts at {epoch, 0}
                     ticket = (uint32_t)atomicAdd(info, 1ull);
                 }
@@ -1214,7 +1215,7 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
                     s2 = 0;
                 }
                 // writer entry {agent, action}: inline in the row block, then the row's spill array, then the overflow list
-                if (!F.evaluate) store_entry(T, info, ticket, i, a, epoch);
+                if (!F.evaluate && !ACC) store_entry(T, info, ticket, i, a, epoch);
                 T.tr_p[i] = p;
                 nxt[i] = s2;
                 if (ENV != 0) F.envw[i] = ew;
@@ -1250,6 +1251,34 @@ __global__ void __launch_bounds__(256, QE_FUSED_MIN_BLOCKS) fused_kernel(Table T
         grid.sync();
         if (clk && k < 10) F.phase_ns[1 + 3 * k] = global_ns();
         if (F.evaluate) continue;  // the table is read-only: nothing to update, the barrier above orders the state buffers
+        if (ACC) {
+            // ---------------- learn_vec (QLO:819-891): every bootstrap and every prediction comes from the table as it
+            // was before this step (the prediction was captured in phase A), the increments are scattered with atomicAdd
+            // (np.add.at accumulates in agent order; atomics in any order -> equal up to fp32 rounding of the sum)
+            for (int base = (tid & ~31); base < n; base += nthreads) {
+                const int i = base + lane;
+                const bool active = i < n;
+                const int ii = active ? i : 0;
+                const uint8_t at = F.tr_a[ii];
+                const bool boot = active && !(at & 0x80);
+                const int s2 = nxt[ii];
+                const uint32_t ew = (ENV == 1) ? F.envw[ii] : 0u;
+                const uint32_t m2 = F.use_masks ? env_mask<ENV>(s2, ew, T.A, F.env_seed) : full;
+                RowGather<LPR> rows;
+                rows.issue(T, s2, boot);
+                const float m = rows.row_max(boot ? m2 : 0u);
+                if (boot && m2 == 0u) atomicOr(T.err, kErrEmpty);
+                // targets = r + gamma * max * (1 - terminated); delta = lr * (targets - prediction)   (QLO:884-891)
+                const float target = __fadd_rn(F.tr_r[ii], boot ? __fmul_rn(F.gamma, m) : 0.0f);
+                if (active) F.tr_r[ii] = __fmul_rn(lr, __fsub_rn(target, __ldcg(T.tr_p + ii)));
+            }
+            grid.sync();
+            if (clk && k < 10) F.phase_ns[2 + 3 * k] = global_ns();
+            for (int i = tid; i < n; i += nthreads) atomicAdd(T.q + (size_t)cur[i] * T.ld + (F.tr_a[i] & 0x7F), F.tr_r[i]);
+            grid.sync();
+            if (clk && k < 10) F.phase_ns[3 + 3 * k] = global_ns();
+            continue;
+        }
 
         // ---------------- phase B1: exact sequential TD update, first pass (agents that wait for nobody finish)
         // Tiles are claimed from a counter (crowded tiles cost several times more than sparse ones); the next claim

@@ -157,6 +157,10 @@ typedef struct {
     /* 1: evaluation loop (BaseRuntime.evaluate_steps / evaluate_episodes, BRT:293-384): select + env step only, the
      * table is not updated (pass explore thresholds of 0 for the reference's deterministic=True, exploration_rate=0) */
     int32_t evaluate;
+    /* TD update of the loop: QE_LEARN_SEQUENTIAL (0; learn -> learn_iter, QLO:893-934, what the reference's trainers
+     * call) or QE_LEARN_ACCUMULATE (1; learn_vec, QLO:819-891: snapshot bootstrap + accumulating scatter with plain
+     * atomics -- equal to the reference up to the fp32 rounding of the order in which increments of one cell are summed) */
+    int32_t learn_mode;
 } qe_run_t;
 
 int qe_fused_steps(qe_engine_t* e, const qe_agents_t* agents, const qe_run_t* run, void* stream);

@@ -1,7 +1,9 @@
-"""Dependency depth of one vector step of the sequential TD update on the C3 workload (CPU analysis, oracle only)."""
+"""Dependency depth of one vector step of the sequential TD update on the C3 workload (analysis aid, CPU only; lives under
+tests/ because it drives the oracle: `python tests/dependency_depth.py <warm-up steps> [agents]`).  Output of the round-1 run:
+profiles/r1_dependency_depth.md."""
 import sys, math, ctypes as C
 import numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from oracle import c_oracle as co, rng as orng
 from oracle.envs import T_INIT
 

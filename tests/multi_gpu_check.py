@@ -1,6 +1,6 @@
 """Sharded / replicated modes over NCCL, one rank per GPU, checked against the C oracle (run under torchrun):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/multi_gpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 """
 import math
 import os

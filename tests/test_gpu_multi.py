@@ -22,7 +22,7 @@ def test_sharded_table_over_nccl():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "MULTI_GPU_CHECK PASS" in res.stdout

@@ -320,3 +320,50 @@ def test_dist_async_train_with_validation(api):  # T-MPI:150-205
     assert len(val) == 2 and all(v == 5.0 for v in val)
     assert [float(h) for h in hist] == [5.0]
     assert rt.exploration_rate_schedule.get_value() == 7.0
+
+
+@pytest.mark.parametrize("s,n", [(3000, 4096), (200000, 2048)])
+def test_fused_accumulate_mode_matches_learn_vec_step_by_step(api, s, n):
+    """``td_update = "accumulate"``: the fused loop with the plain-atomics update = select -> env step -> ``learn_vec``
+    (QLO:819-891).  Checked one vector step at a time against the oracle started from the engine's own table of the
+    step before: actions, rewards, flags and next states bit-exact; the table within 1e-6 (the reference evaluates
+    ``gamma * max * (1 - terminated)`` in float64 because of the int64 factor and rounds on the scatter, the engine
+    works in fp32; the increments of one cell are summed by atomics in any order, np.add.at sums them in agent order)."""
+    from oracle import qlearning as oq
+    from oracle import rng as orng
+    from oracle.envs import HashMDPVec
+
+    a, steps, gamma, lr, eps = 16, 5, 0.9, 0.25, 0.3
+    u = orng.draw_uniforms(5, 0, steps, n, 4)
+    u0 = orng.draw_uniforms(5, 0xFFFFFFFF, 1, n, 4)[0]
+    env = api.env.HashMDPVecEnv(n, s, a, env_seed=3, p_term=0.05)
+    algo = api.QL(s, a, gamma, seed=0)
+    algo.q_table = np.random.default_rng(2).random((s, a), dtype=np.float32)
+    env.attach(algo)
+    states, infos = env.reset_with(u0)
+    algo._rng = env._rng = api.rng.PredrawnUniforms(u)
+    rt = api.rt.SingleThreadQLearning(algo, api.sch.ConstantSchedule(lr), api.sch.ConstantSchedule(eps))
+    rt.td_update = "accumulate"
+    oenv = HashMDPVec(n, s, a, seed=3, p_term=0.05)
+    ostates, _ = oenv.reset(u0)
+    sd = {"states": states, "infos": infos, "rewards": np.zeros(n, dtype=np.float32)}
+    for t in range(steps):
+        q_before = algo.q_table.copy()
+        trace = {}
+        _m, _h, _e, sd = rt.run_steps(1, env, sd, trace=trace)
+        act = oq.select(q_before, ostates["observation"], ostates["action_mask"], eps, u[t])
+        nxt, rew, term, _trunc, _ = oenv.step(act, u[t])
+        np.testing.assert_array_equal(trace["actions"][0][0], act)
+        np.testing.assert_array_equal(trace["rewards"][0][0], rew)
+        np.testing.assert_array_equal(trace["terminated"][0][0].astype(bool), term)
+        np.testing.assert_array_equal(trace["obs"][0][0], nxt["observation"])
+        q_ref = q_before.copy()
+        oq.learn_accumulate(q_ref, ostates["observation"], act, rew, nxt["observation"], term, lr, gamma, nxt["action_mask"])
+        q_gpu = algo.q_table
+        np.testing.assert_allclose(q_gpu, q_ref, rtol=1e-6, atol=1e-6)
+        cells = ostates["observation"].astype(np.int64) * a + act
+        untouched = np.bincount(cells, minlength=s * a).reshape(s, a) == 0
+        np.testing.assert_array_equal(q_gpu[untouched], q_before[untouched])
+        assert not np.array_equal(q_gpu, q_before)
+        algo.q_table = q_ref  # both sides continue from the reference's table
+        ostates = nxt
