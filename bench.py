@@ -202,6 +202,73 @@ def python_port_rate(workload: str, agents: int, steps: int):
     return agents * steps / dt
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_rate(workload: str, agents: int, steps: int, warm: int = 1):
+    """agent-steps/s of the UNMODIFIED reference (pip-installed from /root/reference into baseline/_ref): its own
+    ``OptimalQLearningBase`` (``choose_actions`` / ``learn``, stock float64 table and stock RNGs) driven by its own
+    ``BaseRuntime.run_single_step`` -- the loop body of ``SingleThreadQLearning.run_steps`` (STR:63-64), which itself
+    cannot be imported without gymnasium -- on the NumPy twin of the workload's environment.  Single-threaded, like the
+    reference.  Returns (rate, seconds, description) or None if the reference is not installed."""
+    if not os.path.isdir(os.path.join(REF_DIR, "dist_classicrl")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        from dist_classicrl.algorithms.base_algorithms.q_learning_optimal import OptimalQLearningBase as RefQL
+        from dist_classicrl.algorithms.runtime.base_runtime import BaseRuntime as RefRuntime
+        from dist_classicrl.schedules.constant_schedule import ConstantSchedule as RefConstant
+    except Exception:  # noqa: BLE001
+        return None
+    from oracle import rng as orng
+    from oracle.envs import T_INIT, HashMDPVec, TicTacToeVec
+
+    s, a, _n, _ = WORKLOADS[workload]
+
+    class Loop(RefRuntime):  # the ABC's three abstract hooks; everything that runs is the reference's
+        def init_training(self):
+            return None
+
+        def run_steps(self, steps, env, curr_state_dict):
+            return None
+
+        def close_training(self):
+            return None
+
+    class Env:  # gym-style step(actions) on top of the oracle environment, one row of the uniform stream per step
+        def __init__(self):
+            self.inner = TicTacToeVec(agents) if workload == "c2" else HashMDPVec(agents, s, a, seed=ENV_SEED, p_term=P_TERM)
+            self.slots = 5 if workload == "c2" else 4
+            self.t = 0
+            self.num_envs = agents
+
+        def reset(self):
+            return self.inner.reset(orng.draw_uniforms(STREAM_SEED, T_INIT, 1, agents, self.slots)[0])
+
+        def step(self, actions):
+            u = orng.draw_uniforms(STREAM_SEED, self.t, 1, agents, self.slots)[0]
+            self.t += 1
+            return self.inner.step(actions, u)
+
+    algo = RefQL(s, a, GAMMA, seed=STREAM_SEED)
+    if workload != "c2":
+        algo.q_table = np.random.default_rng(TABLE_SEED).random((s, a))
+    rt = Loop(algo, RefConstant(LR), RefConstant(EPS))
+    env = Env()
+    states, _ = env.reset()
+    rewards = np.zeros(agents, dtype=np.float32)
+    history: list = []
+    for _ in range(warm):
+        states, _ = rt.run_single_step(env, states, rewards, history)
+    t = time.perf_counter()
+    for _ in range(steps):
+        states, _ = rt.run_single_step(env, states, rewards, history)
+    dt = time.perf_counter() - t
+    return agents * steps / dt, dt, ("unmodified reference from baseline/_ref: OptimalQLearningBase.choose_actions/learn driven by "
+                                    "BaseRuntime.run_single_step, stock float64 table and RNGs, NumPy twin of the environment")
+
+
 def run_reference(args) -> dict:
     """`--impl reference`: the CPU restatement of the reference's path, all host threads, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -211,11 +278,32 @@ def run_reference(args) -> dict:
     s, a, n, desc = WORKLOADS[workload]
     # bounded sample: the reference loop is sequential in the agents, so per-agent-step cost does not depend on
     # the batch size; cap the agents so that warm-up + K steps stay within a few minutes
-    agents = min(n, 1 << 20)
     steps = max(1, args.steps)
-    rate, dt = cpu_port_rate(workload, agents, steps, warm=min(args.warmup, 3) or 1)
+    # the reference itself (single-threaded Python: ~25 us per agent-step whatever the batch size) on a bounded sample
+    ref_agents = min(n, 1 << 12)
+    ref = reference_rate(workload, ref_agents, steps, warm=min(args.warmup, 2) or 1)
+    agents = min(n, 1 << 20)
+    port_rate, port_dt = cpu_port_rate(workload, agents, min(steps, 12), warm=1)
     cores = os.cpu_count() or 1
-    sample = f"{steps} vector steps x {agents} agents of the same workload (C port of the reference loop, OpenMP select+env, sequential learn)"
+    port_sample = f"{min(steps, 12)} vector steps x {agents} agents of the same workload (C port of the reference loop, OpenMP select+env, sequential learn)"
+    if ref is not None:
+        rate, dt, how = ref
+        return {
+            "impl": "reference", "metric": "agent-steps/s", "value": rate, "unit": "agent-steps/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{workload}: {desc}", "states": s, "actions": a, "agents_per_gpu": n, "agents": n * args.gpus,
+                       "sample_agents": ref_agents, "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM,
+                       "ms_per_full_step_scaled": dt / steps * 1e3 * (n / ref_agents),
+                       "note": "a step of this arm is one vector step of the SAMPLE (sample_agents agents); the reference's cost per agent-step does not depend on the batch size"},
+            "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": 1, "kind": "reference",
+                             "sample": f"{steps} vector steps x {ref_agents} agents of the same workload; {how}",
+                             "c_port_value": port_rate, "c_port_cores": cores, "c_port_sample": port_sample},
+            "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+    rate, dt, sample = port_rate, port_dt, port_sample
+    steps = min(steps, 12)
     return {
         "impl": "reference", "metric": "agent-steps/s", "value": rate, "unit": "agent-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
@@ -507,7 +595,16 @@ def run_ours(args) -> dict | None:
         cpu_rate, cpu_dt = cpu_port_rate(workload, cpu_agents, cpu_steps)
         py_agents, py_steps = (n, 50) if workload == "c2" else (1 << 13, 4)
         py_rate = python_port_rate(workload, py_agents, py_steps)
-        cpu_baseline = {"value": cpu_rate, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+        ref = reference_rate(workload, min(n, 1 << 12), 4)
+        if ref is not None:
+            cpu_baseline = {"value": ref[0], "unit": "agent-steps/s", "cores": 1, "kind": "reference",
+                            "sample": f"4 vector steps x {min(n, 1 << 12)} agents ({ref[1]:.1f} s); {ref[2]}",
+                            "c_port_value": cpu_rate, "c_port_cores": os.cpu_count() or 1,
+                            "c_port_sample": f"{cpu_steps} vector steps x {cpu_agents} agents, C port of the reference loop ({cpu_dt:.1f} s)",
+                            "python_port_value": py_rate, "python_port_cores": 1,
+                            "python_port_sample": f"{py_steps} vector steps x {py_agents} agents, NumPy/Python restatement"}
+        else:
+            cpu_baseline = {"value": cpu_rate, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
                         "sample": f"{cpu_steps} vector steps x {cpu_agents} agents, C port of the reference loop ({cpu_dt:.1f} s)",
                         "python_port_value": py_rate, "python_port_cores": 1,
                         "python_port_sample": f"{py_steps} vector steps x {py_agents} agents, NumPy/Python restatement (per-agent Python learn loop like the reference)"}
