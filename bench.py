@@ -75,6 +75,7 @@ class ClockSampler:
         self.smax = None
         self._stop = threading.Event()
         self._thread = None
+        self.period = float(os.environ.get("BENCH_CLOCK_PERIOD_MS", "1.0")) * 1e-3  # NVML polling period
 
     def _physical_index(self) -> int:
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -113,7 +114,7 @@ class ClockSampler:
                 self.samples.append((int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(reasons_fn(h))))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.0005)
+            time.sleep(self.period)
 
     def _read(self) -> None:
         for line in self.proc.stdout:
