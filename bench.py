@@ -116,6 +116,18 @@ class ClockSampler:
                 pass
             time.sleep(self.period)
 
+    def sample_now(self) -> None:
+        """One sample from the calling thread (the timed loop calls it between launches: the GPU is busy with the work
+        already queued, so the host-side query costs the measurement nothing and cannot be starved like the poller)."""
+        if self.nvml is None:
+            return
+        pynvml, h = self.nvml
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.samples.append((int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(reasons_fn(h))))
+        except Exception:  # noqa: BLE001
+            pass
+
     def _read(self) -> None:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
@@ -430,10 +442,14 @@ def run_ours(args) -> dict | None:
         if rep is not None:
             rep.sync()
     capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
-    sync_all()
+    if rep is not None and os.environ.get("BENCH_SYNC_TRACE"):
+        rep.trace_events = []
+    # the sampler starts BEFORE the barrier that opens the timed region: NVML initialisation takes milliseconds, and a
+    # rank 0 that enters the region late makes every other rank wait for it at the first all-reduce
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    sync_all()
     launches0 = lib.qe_kernel_launches(algo.handle)
     kernel_events = []
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -446,9 +462,20 @@ def run_ours(args) -> dict | None:
         kernel_events.append((k, e0, e1))
         if rep is not None:
             rep.sync()
+        if rank == 0:
+            sampler.sample_now()
     e_end.record(stream)
     sync_all()
     capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
+    if rep is not None and getattr(rep, "trace_events", None):
+        tr = rep.trace_events
+        parts = [sum(e[j].elapsed_time(e[j + 1]) for e in tr) / len(tr) for j in range(3)]
+        gaps = [kernel_events[j + 1][1].elapsed_time(kernel_events[j + 1][2]) for j in range(len(kernel_events) - 1)]
+        after = [tr[j][3].elapsed_time(kernel_events[j + 1][1]) for j in range(min(len(tr), len(kernel_events) - 1))]
+        before = [kernel_events[j][2].elapsed_time(tr[j][0]) for j in range(min(len(tr), len(kernel_events)))]
+        sys.stderr.write(f"[rank {rank}] sync: delta {parts[0]:.3f} ms, all-reduce {parts[1]:.3f} ms, merge {parts[2]:.3f} ms; "
+                         f"launch->sync gap {sum(before) / len(before):.3f} ms, sync->launch gap {sum(after) / max(1, len(after)):.3f} ms; "
+                         f"launches {[round(e0.elapsed_time(e1), 2) for _, e0, e1 in kernel_events]}\n")
     total_ms = max_over_ranks(e_begin.elapsed_time(e_end))
     kernel_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in kernel_events)
     gpu_launches = int(lib.qe_kernel_launches(algo.handle) - launches0)

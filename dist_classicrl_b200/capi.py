@@ -78,6 +78,7 @@ SIGNATURES = {
     "qe_kernel_launches": (i64, [vp]),
     "qe_fused_grid_blocks": (i32, [vp]),
     "qe_fused_form": (i32, [vp]),
+    "qe_set_fused_form": (C.c_int, [vp, i32]),
     "qe_fused_phase_ns": (i32, [vp, vp, i32]),
     "qe_debug_gridsync_us": (C.c_double, [vp, i32]),
     "qe_debug_counters": (C.c_int, [vp, vp, i32]),

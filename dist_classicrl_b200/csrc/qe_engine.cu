@@ -237,6 +237,12 @@ int32_t qe_table_stride(qe_engine_t* e) { return e->ld; }
 int64_t qe_kernel_launches(qe_engine_t* e) { return e->launches; }
 int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
 int32_t qe_fused_form(qe_engine_t* e) { return e->current; }
+int qe_set_fused_form(qe_engine_t* e, int32_t form) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (form < 0 || form > 2) return fail(QE_ERR_ARG, "form must be 0 (writer lists), 1 (per-step sort) or 2 (pick by measurement)");
+    e->strategy = form;
+    return QE_OK;
+}
 int qe_debug_counters(qe_engine_t* e, uint64_t* out8_host, int32_t reset) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (!e->X.dbg) return fail(QE_ERR_ARG, "no counters");

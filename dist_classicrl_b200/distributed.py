@@ -30,6 +30,8 @@ Transports: :class:`TorchDistTransport` (NCCL on GPUs, gloo in the CPU tests) an
 
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 import threading
@@ -519,6 +521,11 @@ class ReplicatedQLearning:
         self.base = torch.empty(shape, dtype=torch.float32, device=self.dev)
         self.delta = torch.empty(shape, dtype=torch.float32, device=self.dev)
         self.syncs = 0
+        # Merged replicas learn world_size times as fast, so agents herd onto the same rows sooner: the per-step sort is
+        # the form of the exact update whose cost does not grow with the crowd, and a form that is the same on every rank
+        # keeps the ranks in step at the all-reduce (QE_SORTED in the environment overrides).
+        if transport.world_size > 1 and "QE_SORTED" not in os.environ:
+            capi.check(capi.lib().qe_set_fused_form(algo.handle, 1))
         self.rebase()
 
     def _stream(self):
@@ -532,9 +539,20 @@ class ReplicatedQLearning:
     def sync(self) -> None:
         lib, h = capi.lib(), self.algorithm.handle
         self.algorithm._before_device_op()
+        trace = getattr(self, "trace_events", None)  # development aid: [(start, after delta, after all-reduce, after merge)]
+        ev = [_torch().cuda.Event(enable_timing=True) for _ in range(4)] if trace is not None else None
+        if ev:
+            ev[0].record()
         capi.check(lib.qe_table_delta_dense(h, self.base.data_ptr(), self.delta.data_ptr(), self._stream()))
+        if ev:
+            ev[1].record()
         self.tp.all_reduce_sum_(self.delta)
+        if ev:
+            ev[2].record()
         capi.check(lib.qe_table_merge_dense(h, self.base.data_ptr(), self.delta.data_ptr(), self._stream()))
+        if ev:
+            ev[3].record()
+            trace.append(ev)
         self.algorithm._device_wrote()
         self.syncs += 1
 

@@ -195,6 +195,11 @@ int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch
 /* form of the TD update the last fused launch used: 0 = writer lists, 1 = per-step sort (both exact; the engine times
  * its launches and keeps the faster one; QE_SORTED=0/1 in the environment pins it) */
 int32_t qe_fused_form(qe_engine_t* e);
+/* Which exact form of the TD update the fused loop uses: 0 = writer lists, 1 = per-step sort, 2 = keep timing both and
+ * use the faster one (default; the QE_SORTED environment variable sets the initial value).  Both forms give identical
+ * results.  The replicated multi-GPU mode pins form 1 on every rank: merged replicas learn G times as fast, agents herd
+ * sooner, and ranks that probe at different moments would wait for each other at the all-reduce. */
+int qe_set_fused_form(qe_engine_t* e, int32_t form);
 /* phase clock of the last fused launch (synchronous): out_host[0] = %globaltimer (ns) at kernel start, then for each
  * of the first 10 vector steps the time after phase A (select + env step + writer registration), after phase B1 (TD
  * update, first pass) and after phase B2 (TD update, deferred agents).  Returns the number of values written. */
