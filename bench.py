@@ -549,7 +549,7 @@ def run_ours(args) -> dict | None:
     algo, env = make()
     rt = SingleThreadQLearning(algo, ConstantSchedule(LR), ConstantSchedule(EPS))
     rt.history_mode = "summary"
-    runner = D.ReplicatedQLearning(rt, tp, sync_every=1) if tp is not None else rt
+    runner = D.ReplicatedQLearning(rt, tp, sync_every=SYNC_EVERY, carry_over=True) if tp is not None else rt
     Ke = min(K, 20)
     slots = env.slots
     u_host = torch.empty((W + Ke, n, slots), dtype=torch.int32).pin_memory()
@@ -568,7 +568,7 @@ def run_ours(args) -> dict | None:
     h2d = n * slots * 4 + n * 4 + 12  # the step's uniforms + the agents' running returns (state dict) + eps/lr of the step
     d2h = n * 4 + 16                  # the running returns + {sum, count} of the episodes that finished in the step
     e2e = {"value": world * n * Ke / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-           "steps": Ke, "api": ("ReplicatedQLearning(sync_every=1)." if tp is not None else "SingleThreadQLearning.") +
+           "steps": Ke, "api": (f"ReplicatedQLearning(sync_every={SYNC_EVERY}, carry_over=True)." if tp is not None else "SingleThreadQLearning.") +
            "run_steps(1, env, state_dict): the step's pre-drawn uniforms (PredrawnUniforms, pinned host memory) and the state dict's running returns go host->device, the returns and the episode statistics come back, every step"}
     del algo, env, runner, rt
 

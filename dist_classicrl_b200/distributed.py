@@ -511,7 +511,7 @@ class ReplicatedQLearning:
     vector steps by an all-reduce of their deltas (config 5).  ``runtime`` is a single-GPU trainer
     (``SingleThreadQLearning``) whose ``run_steps`` executes the fused loop."""
 
-    def __init__(self, runtime, transport: Transport, sync_every: int = 8) -> None:
+    def __init__(self, runtime, transport: Transport, sync_every: int = 8, carry_over: bool = False) -> None:
         torch = _torch()
         self.runtime, self.tp, self.sync_every = runtime, transport, int(sync_every)
         algo = runtime.algorithm
@@ -521,6 +521,9 @@ class ReplicatedQLearning:
         self.base = torch.empty(shape, dtype=torch.float32, device=self.dev)
         self.delta = torch.empty(shape, dtype=torch.float32, device=self.dev)
         self.syncs = 0
+        # carry_over: the period counts vector steps ACROSS run_steps calls (a caller that advances one step per call
+        # still merges every sync_every steps) instead of merging at the end of every call
+        self.carry_over, self._since_sync = bool(carry_over), 0
         # Merged replicas learn world_size times as fast, so agents herd onto the same rows sooner: the per-step sort is
         # the form of the exact update whose cost does not grow with the crowd, and a form that is the same on every rank
         # keeps the ranks in step at the all-reduce (QE_SORTED in the environment overrides).
@@ -563,10 +566,13 @@ class ReplicatedQLearning:
         state = curr_state_dict
         done = 0
         while done < steps:
-            k = min(self.sync_every, steps - done)
+            k = min(self.sync_every - self._since_sync, steps - done)
             _, hist, env, state = self.runtime.run_steps(k, env, state)
             history.extend(hist)
-            self.sync()
             done += k
+            self._since_sync += k
+            if self._since_sync >= self.sync_every or (done == steps and not self.carry_over):
+                self.sync()
+                self._since_sync = 0
         mean = float(np.mean(history)) if history else 0.0
         return mean, history, env, state

@@ -86,7 +86,8 @@ def test_sharded_table_matches_oracle(capi, world, S, A, N, steps):
         assert np.array_equal(other[0], table)
 
 
-def test_replicated_table_delta_rule(capi):
+@pytest.mark.parametrize("stepwise", [False, True])
+def test_replicated_table_delta_rule(capi, stepwise):
     from dist_classicrl_b200 import distributed as D
     from dist_classicrl_b200.algorithms.base_algorithms.q_learning_optimal import OptimalQLearningBase
     from dist_classicrl_b200.algorithms.runtime import SingleThreadQLearning
@@ -105,8 +106,14 @@ def test_replicated_table_delta_rule(capi):
         env.attach(algo)
         rt = SingleThreadQLearning(algo, ConstantSchedule(LR), ConstantSchedule(EPS))
         rt.history_mode = "summary"
-        rep = D.ReplicatedQLearning(rt, tp, sync_every=sync_every)
-        rep.run_steps(sync_every * chunks, env)
+        if stepwise:  # one vector step per call, the merge period carried across the calls: same merges, same result
+            rep = D.ReplicatedQLearning(rt, tp, sync_every=sync_every, carry_over=True)
+            state = None
+            for _ in range(sync_every * chunks):
+                _m, _h, env, state = rep.run_steps(1, env, state)
+        else:
+            rep = D.ReplicatedQLearning(rt, tp, sync_every=sync_every)
+            rep.run_steps(sync_every * chunks, env)
         return np.array(algo.q_table, copy=True), env.states.cpu().numpy(), rep.syncs
 
     out = D.run_loopback(world, body)
