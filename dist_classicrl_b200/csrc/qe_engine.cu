@@ -57,7 +57,7 @@ struct qe_engine {
     // a row) and the per-step sort (qe_sorted.cuh; best once agents herd).  Both give identical results, so the engine
     // times its launches and keeps using the faster form, trying the other one every kProbeEvery launches.
     int strategy = 2;        // QE_SORTED env: 0 = writer lists only, 1 = sorted only, 2 (default) = pick by measurement
-    int current = 0, since_probe = 0, timed_kind = -1, n_timed[2] = {0, 0};
+    int current = 0, since_probe = 0, timed_kind = -1, auto_launches = 0, auto_form = 0;  // state of pick_form (strategy 2)
     double timed_work = 0.0, rate[2] = {0.0, 0.0};  // agent-steps per millisecond of the last timed launch of each form
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
@@ -671,24 +671,44 @@ int qe_mdp_step(qe_engine_t* e, int32_t* states, const int32_t* actions, int64_t
 // ---------------------------------------------------------------------------------------------- fused loop
 }  // extern "C"
 constexpr int kProbeEvery = 12;
-static int pick_form(qe_engine* e, const FusedArgs& F) {
-    if (e->timed_kind >= 0 && cudaEventQuery(e->ev1) == cudaSuccess) {  // the last timed launch has finished: book it
-        float ms = 0.0f;
-        // (the first launch of a form pays for module loading and cold caches: it is not a measurement)
-        if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess && ms > 0.0f && ++e->n_timed[e->timed_kind] >= 2)
-            e->rate[e->timed_kind] = e->timed_work / ms;
-        e->timed_kind = -1;
-    }
-    (void)cudaGetLastError();
+// Which exact form the next fused launch uses (strategy 2).  Agents herd as the table is learned, so the faster form
+// changes during a run and a comparison is only worth something if both forms were timed at (nearly) the same training
+// progress: the first four launches are {lists cold, lists timed, sort cold, sort timed} (a form's first launch pays for
+// module loading and scratch allocation), and every kProbeEvery launches after that the other form and then the current
+// one are timed in two ADJACENT launches.  A timed launch is collected by the next call (it waits for the event: two
+// launches out of kProbeEvery); all other launches carry no events at all.  *time_it: record events around this launch.
+static int pick_form(qe_engine* e, const FusedArgs& F, bool* time_it) {
+    *time_it = false;
     if (e->state_base != 0 || e->A > 32 || !e->X.seg) return 0;
     if (F.accumulate) return 0;  // the plain-atomics update lives in fused_kernel
     if (e->strategy == 0 || e->strategy == 1) return e->strategy;
     if (F.evaluate) return e->current;
-    if (e->n_timed[0] < 2) return 0;
-    if (e->n_timed[1] < 2) return 1;
-    const int best = e->rate[1] > e->rate[0] ? 1 : 0;
-    if (++e->since_probe >= kProbeEvery) {  // the workload drifts (agents herd as the table is learned): look again
+    if (e->timed_kind >= 0) {  // collect the launch timed last
+        float ms = 0.0f;
+        if (cudaEventSynchronize(e->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess && ms > 0.0f)
+            e->rate[e->timed_kind] = e->timed_work / ms;
+        e->timed_kind = -1;
+        (void)cudaGetLastError();
+    }
+    const int seq = e->auto_launches < 1000000 ? e->auto_launches++ : e->auto_launches;  // launches of strategy 2 so far
+    if (seq < 4) {                    // lists cold, lists timed, sort cold, sort timed
+        *time_it = (seq & 1) != 0;
+        return seq >> 1;
+    }
+    if (seq == 4) e->auto_form = e->rate[1] > e->rate[0] ? 1 : 0;
+    int best = e->auto_form;
+    if (e->since_probe == -1) {  // second half of a probe: the other form was timed by the last launch, now the current one
+        e->since_probe = -2;
+        *time_it = true;
+        return best;
+    }
+    if (e->since_probe == -2) {  // both are in: decide
+        best = e->auto_form = e->rate[1] > e->rate[0] ? 1 : 0;
         e->since_probe = 0;
+    }
+    if (++e->since_probe >= kProbeEvery) {
+        e->since_probe = -1;
+        *time_it = true;
         return best ^ 1;
     }
     return best;
@@ -698,8 +718,8 @@ template <int ENV, int LPR>
 static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     int blocks = 0;
     Table T = e->T;
-    const int form = pick_form(e, F);
-    const bool timed = !F.evaluate && !F.accumulate && e->timed_kind < 0;
+    bool timed = false;
+    const int form = pick_form(e, F, &timed);
     if (timed) CK(cudaEventRecord(e->ev0, st));
     if (form == 1) {
         int rc = coop_blocks(e, fused_sorted_kernel<ENV, LPR>, (long long)F.n, &blocks);

@@ -171,3 +171,36 @@ def test_both_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form
         assert np.array_equal(r.table(), q_o)
     finally:
         r.close()
+
+
+def test_automatic_form_selection_switches_forms_and_stays_exact(capi, monkeypatch):
+    """Default strategy (no QE_SORTED): the engine's first four launches are {writer lists cold, timed, sort cold,
+    timed}, then it keeps the faster form and times both again in two adjacent launches every 12 launches.  Whatever
+    it picks, the results are the oracle's; qe_set_fused_form pins and releases the choice."""
+    monkeypatch.delenv("QE_SORTED", raising=False)
+    S, A, N, launches, k, seed = 4000, 16, 60_000, 32, 1, 4
+    q_o, st_o, rew_o, _ = _oracle(S, A, N, launches * k + 4, seed, 1)
+    r = Run(capi, S, A, N, seed, 1)
+    try:
+        forms = []
+        for _ in range(launches):
+            r.steps(k)
+            forms.append(int(capi.lib().qe_fused_form(r.h)))
+        assert forms[:4] == [0, 0, 1, 1]
+        steady = forms[4]
+        assert forms[4:15] == [steady] * 11            # launches 5..15 use the pick
+        assert forms[15:17] == [steady ^ 1, steady]    # the probe: the other form, then the current one, adjacent
+        assert set(forms[17:28]) <= {0, 1} and len(set(forms[17:28])) == 1
+        capi.check(capi.lib().qe_set_fused_form(r.h, 0))
+        r.steps(2)
+        assert capi.lib().qe_fused_form(r.h) == 0
+        capi.check(capi.lib().qe_set_fused_form(r.h, 1))
+        r.steps(2)
+        assert capi.lib().qe_fused_form(r.h) == 1
+        with pytest.raises(ValueError):
+            capi.check(capi.lib().qe_set_fused_form(r.h, 3))
+        assert np.array_equal(r.states.cpu().numpy(), st_o)
+        assert np.array_equal(r.ep.cpu().numpy(), rew_o)
+        assert np.array_equal(r.table(), q_o)
+    finally:
+        r.close()
