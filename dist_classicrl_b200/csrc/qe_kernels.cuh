@@ -606,15 +606,24 @@ __global__ void select_generic_kernel(Table T, const int32_t* __restrict__ state
 #ifndef QE_FUSED_MIN_BLOCKS
 #define QE_FUSED_MIN_BLOCKS 4
 #endif
-constexpr int kFastTiles = 8;   // tiles per statically owned group of the sweep over deferred records
+// Tiles per statically owned group of the sweep over deferred records: 8, or as many as it takes to give every warp
+// of the grid ONE group when that is more (config 4's 4M agents on 4736 warps: 28 -- several groups per warp re-walk
+// the tile masks and leave some warps with one group more than others: 4.0 -> 4.5 G agent-steps/s); at most 32 (one
+// tile mask per lane).  Not fewer than 8: on config 3 (7 would do) the warps left without a group carry the in-order
+// pass for the crowded agents, which is on the critical path -- spreading the sweeps over all warps cost 30 us a step.
+__device__ __forceinline__ int fast_tiles(int n) {
+    const int ntiles = (n + 31) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    return min(32, max(8, (ntiles + nwarps - 1) / nwarps));
+}
 constexpr int kSlowTiles = 16;  // tiles per dynamically claimed group of the in-order pass
 
 // (a) Sweeps.  Every warp owns a fixed set of tile groups.  One sweep visits the still-deferred agents of those groups,
 // 32 per batch: load the record, poll every predecessor once, finish the agent if all of them have published, clear
 // its bit.  Nobody ever waits, so there is no ordering requirement; the DAG drains level by level.
-template <typename Dummy = void>
-__device__ __forceinline__ int sweep_deferred(const Table& T, int n, const int32_t* cur, float lr, float gamma, uint32_t epoch) {
+template <int FT>  // FT > 0: group size known at compile time (the common 8); 0: ft_rt
+__device__ __forceinline__ int sweep_deferred_impl(const Table& T, int n, const int32_t* cur, float lr, float gamma, uint32_t epoch, int ft_rt) {
     const int lane = threadIdx.x & 31;
+    const int kFastTiles = FT > 0 ? FT : ft_rt;
     const int ntiles = (n + 31) >> 5, ngroups = (ntiles + kFastTiles - 1) / kFastTiles;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     int left = 0;  // agents of this warp still deferred after the sweep
@@ -668,6 +677,12 @@ __device__ __forceinline__ int sweep_deferred(const Table& T, int n, const int32
     return left;
 }
 
+template <typename Dummy = void>
+__device__ __forceinline__ int sweep_deferred(const Table& T, int n, const int32_t* cur, float lr, float gamma, uint32_t epoch) {
+    const int ft = fast_tiles(n);
+    return ft == 8 ? sweep_deferred_impl<8>(T, n, cur, lr, gamma, epoch, 8) : sweep_deferred_impl<0>(T, n, cur, lr, gamma, epoch, ft);
+}
+
 // Once at most 32 deferred agents are left to a warp they move into its lanes and are polled back to back (the hop
 // from a predecessor's publication to the dependant's own costs one L2 round trip instead of one sweep).
 struct ResidentLanes {
@@ -677,6 +692,7 @@ struct ResidentLanes {
     bool busy;
     __device__ __forceinline__ void load(const Table& T, int n) {
         const int lane = threadIdx.x & 31;
+        const int kFastTiles = fast_tiles(n);
         const int ntiles = (n + 31) >> 5, ngroups = (ntiles + kFastTiles - 1) / kFastTiles;
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
         busy = false;
