@@ -489,7 +489,15 @@ def run_ours(args) -> dict | None:
     kernel_events = []
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_begin.record(stream)
-    for k in chunks(K):
+    # long windows: the workload drifts, so the pinned form is looked at again every 12 launches -- the other form, then
+    # the current one, in two adjacent launches of the window (they are ordinary steps of the run), like the engine's
+    # own selection does
+    cur_form = int(lib.qe_fused_form(algo.handle))
+    reprobes = []
+    for j, k in enumerate(chunks(K)):
+        probing = calibration is not None and j >= 12 and (j % 12) in (0, 1)
+        if probing:
+            capi.check(lib.qe_set_fused_form(algo.handle, cur_form ^ 1 if j % 12 == 0 else cur_form))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         launch(k)
@@ -497,6 +505,14 @@ def run_ours(args) -> dict | None:
         kernel_events.append((k, e0, e1))
         if rep is not None:
             rep.sync()
+        if probing and j % 12 == 1:
+            e1.synchronize()
+            (ka, a0, a1), (kb, b0, b1) = kernel_events[-2], kernel_events[-1]
+            other, mine = a0.elapsed_time(a1) / ka, b0.elapsed_time(b1) / kb
+            if other < mine:
+                cur_form ^= 1
+            capi.check(lib.qe_set_fused_form(algo.handle, cur_form))
+            reprobes.append({"launch": j, "other_ms_per_step": other, "current_ms_per_step": mine, "now": ["writer lists", "per-step sort"][cur_form]})
     e_end.record(stream)
     sync_all()
     capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
@@ -680,7 +696,7 @@ def run_ours(args) -> dict | None:
            "timing": "CUDA events around the K timed steps (max over ranks); no L2 flush: the working set (256 MB of row blocks + "
                      "~60 MB of per-agent arrays) is larger than the 126 MB L2",
            "grid_blocks": grid_blocks, "td_update_form_at_end_of_window": fused_form, "timed_window": f"vector steps {W}..{W + K} of the run",
-           "td_update_form_calibration": calibration, "late_training": late}
+           "td_update_form_calibration": calibration, "td_update_form_reprobes": reprobes or None, "late_training": late}
     out = {
         "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
