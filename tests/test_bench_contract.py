@@ -30,3 +30,39 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_our_arm_prints_the_full_contract_line():
+    """One short run of the real thing on the GPU: every key the driver and the judge read is there and consistent."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "16", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "cpu_baseline", "atomics_mode"):
+        assert key in d, key
+    assert d["metric"] == "agent-steps/s" and d["n_gpus"] == 1 and d["steps"] == 16 and d["warmup"] >= 3
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("c3:") and "model" not in d["config"]
+    n = d["config"]["agents"]
+    assert abs(d["value"] - n / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["algorithmic_bytes_per_agent_step"] == 8 * d["config"]["actions"] + 12
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e9) <= 1e-6 * r["achieved"]
+    assert 0.0 < r["frac"] < 1.0 and (r["traffic"] is None or r["traffic"] > 0)
+    e = d["e2e"]
+    assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] >= n * 16 and e["d2h_bytes_per_step"] >= n * 4
+    assert d["gpu_launches"] == 2  # 16 steps = two fused launches of 8
+    c = d["clocks"]
+    assert c["samples"] >= 1 and c["sm_mhz"] and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1 and cb["sample"]
+    assert d["atomics_mode"]["value"] > d["value"]  # dropping the ordering guarantee is never slower
+    assert d["config"]["td_update_form_calibration"]["picked"] in ("writer lists", "per-step sort")
