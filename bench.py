@@ -661,7 +661,7 @@ def run_ours(args) -> dict | None:
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(workload)
+            traffic = json.load(open(tpath)).get(workload + ("_sorted" if fused_form == "per-step sort" else ""))
         except Exception:  # noqa: BLE001
             traffic = None
     kname = ("fused_sorted_kernel" if fused_form == "per-step sort" else "fused_kernel") + ("<MDP,2>" if workload != "c2" else "<TTT,2>")
