@@ -371,6 +371,8 @@ def run_ours(args) -> dict | None:
     # the engine times its first launches of both forms of the TD update before it settles on one: give it five
     # launches of warm-up at least
     K, W = args.steps, max(3, args.warmup, 5 * SYNC_EVERY)
+    # 128 TicTacToe agents take ~11 us per vector step: only long launches amortise the ~40 us a launch costs
+    per_launch = 256 if (workload == "c2" and world == 1) else SYNC_EVERY
     stream = torch.cuda.current_stream()
 
     def sync_all():
@@ -407,6 +409,8 @@ def run_ours(args) -> dict | None:
 
     # ---------------- device-resident throughput: SYNC_EVERY vector steps per launch (+ table merge when N > 1)
     algo, env = make()
+    if workload == "c2" and "QE_SORTED" not in os.environ:
+        capi.check(lib.qe_set_fused_form(algo.handle, 0))  # a per-step sort of 128 agents is all barrier
     ep_ret = torch.zeros(n, dtype=torch.float32, device=dev)
     ag = env.agents_struct(ep_ret)
     stats = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -438,7 +442,7 @@ def run_ours(args) -> dict | None:
     def chunks(total):
         out, left = [], total
         while left > 0:
-            out.append(min(SYNC_EVERY, left))
+            out.append(min(per_launch, left))
             left -= out[-1]
         return out
 
@@ -692,7 +696,7 @@ def run_ours(args) -> dict | None:
     cfg = {"workload": f"{workload}: {desc}" + (f", one replica per GPU, Q-delta all-reduce every {SYNC_EVERY} steps (BASELINE config 5)" if world > 1 else ""),
            "states": s, "actions": a, "agents_per_gpu": n, "agents": n * world, "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM,
            "table_init": "uniform[0,1)" if workload != "c2" else "zeros", "rng": "on-device counter stream",
-           "steps_per_launch": SYNC_EVERY,
+           "steps_per_launch": per_launch,
            "timing": "CUDA events around the K timed steps (max over ranks); no L2 flush: the working set (256 MB of row blocks + "
                      "~60 MB of per-agent arrays) is larger than the 126 MB L2",
            "grid_blocks": grid_blocks, "td_update_form_at_end_of_window": fused_form, "timed_window": f"vector steps {W}..{W + K} of the run",
