@@ -1,11 +1,5 @@
-"""Constant schedule (reference: schedules/constant_schedule.py:6-12)."""
+"""Import path of the reference (``schedules/constant_schedule.py``); the class lives in ``schedules/core.py``."""
 
-from dist_classicrl_b200.schedules.base_schedules import BaseSchedule
+from dist_classicrl_b200.schedules.core import ConstantSchedule
 
-
-class ConstantSchedule(BaseSchedule):
-    def __init__(self, value: float) -> None:
-        super().__init__(value=value, min_value=value)
-
-    def update(self, steps: int) -> None:
-        return None
+__all__ = ["ConstantSchedule"]
