@@ -11,6 +11,7 @@
 #include "../../include/qe_engine.h"
 #include "qe_kernels.cuh"
 #include "qe_sorted.cuh"
+#include "qe_pipe.cuh"
 #include "qe_radix.cuh"
 
 using namespace qe;
@@ -35,6 +36,7 @@ struct qe_engine {
     float gamma = 0.0f;
     Table T{};               // T.q is biased by -state_base rows: kernels index it with GLOBAL state ids
     float* q_real = nullptr; // the allocation (row 0 = state `state_base`)
+    uint32_t* info_real = nullptr;  // writer info of the list form (ensure_info)
     int64_t state_base = 0;
     const uint32_t* agent_ids = nullptr;  // optional global ids of the local agents (uniform stream), device
     int cap = 0;             // per-agent scratch capacity
@@ -52,11 +54,13 @@ struct qe_engine {
     int sched_cap = 0;
     uint32_t step = 0;       // global step counter (epoch / tag source)
     SortedScratch X{};       // scratch of the sorted fused loop (qe_sorted.cuh)
+    PipeScratch P{};         // scratch of the pipelined fused loop (qe_pipe.cuh)
+    int pipe_sorters = 0;    // P.ghist was sized for this many sorting warps (one per block)
     int sorted_grid = 0;     // ghist was sized for this many blocks
     // The fused loop has two exact forms of the TD update: writer lists (qe_kernels.cuh; best while few agents share
     // a row) and the per-step sort (qe_sorted.cuh; best once agents herd).  Both give identical results, so the engine
     // times its launches and keeps using the faster form, trying the other one every kProbeEvery launches.
-    int strategy = 2;        // QE_SORTED env: 0 = writer lists only, 1 = sorted only, 2 (default) = pick by measurement
+    int strategy = 3;        // 0 = writer lists, 1 = per-step sort, 2 = time both and keep the faster, 3 (default) = target pipeline (QE_FORM / QE_SORTED env)
     int current = 0, since_probe = 0, timed_kind = -1, auto_launches = 0, auto_form = 0;  // state of pick_form (strategy 2)
     double timed_work = 0.0, rate[2] = {0.0, 0.0};  // agent-steps per millisecond of the last timed launch of each form
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -110,7 +114,52 @@ static int ensure_agents(qe_engine* e, int n) {
         CK(cudaMemset(X.targ, 0, sizeof(uint64_t) * cap));
         CK(cudaMemset(X.mhist, 0, sizeof(uint64_t) * cap));
     }
+    {
+        PipeScratch& P = e->P;
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(P.rec[b]); cudaFree(P.pos[b]); cudaFree(P.kv[b]);
+            P.rec[b] = nullptr; P.pos[b] = nullptr; P.kv[b] = nullptr;
+        }
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaMalloc(&P.rec[b], sizeof(uint4) * (size_t)cap));
+            CK(cudaMalloc(&P.pos[b], sizeof(int32_t) * cap));
+            CK(cudaMalloc(&P.kv[b], sizeof(int2) * (size_t)cap));
+            CK(cudaMemset(P.rec[b], 0xFF, sizeof(uint4) * (size_t)cap));
+        }
+    }
     e->cap = cap;
+    return QE_OK;
+}
+// state-indexed scratch of the pipelined form (segment bounds, two parities), allocated at its first launch
+static int ensure_pipe(qe_engine* e, int sorters) {
+    PipeScratch& P = e->P;
+    if (!P.seg[0]) {
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaMalloc(&P.seg[b], sizeof(uint2) * (size_t)e->S));
+            CK(cudaMemset(P.seg[b], 0, sizeof(uint2) * (size_t)e->S));
+        }
+        CK(cudaMalloc(&P.rowtot, sizeof(int) * kRadix));
+        CK(cudaMalloc(&P.ctr, 64 * sizeof(unsigned int)));
+        int bits = 1;
+        while (bits < 31 && (1ll << bits) < e->S) ++bits;
+        P.passes = (bits + kRadixBits - 1) / kRadixBits;
+    }
+    if (sorters > e->pipe_sorters) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(P.ghist);
+        P.ghist = nullptr;
+        CK(cudaMalloc(&P.ghist, sizeof(int) * kRadix * (size_t)sorters));
+        e->pipe_sorters = sorters;
+    }
+    return QE_OK;
+}
+// writer info of the list form: allocated (zeroed: epoch 0 never matches) the first time a writer-list kernel runs
+static int ensure_info(qe_engine* e) {
+    if (e->info_real || e->T.info_ld == 0) return QE_OK;
+    const size_t bytes = sizeof(uint32_t) * (size_t)e->S * e->T.info_ld;
+    CK(cudaMalloc(&e->info_real, bytes));
+    CK(cudaMemset(e->info_real, 0, bytes));
+    e->T.info = e->info_real - (size_t)e->state_base * (size_t)e->T.info_ld;
     return QE_OK;
 }
 static int ensure_stage(qe_engine* e, size_t bytes) {
@@ -165,18 +214,14 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     e->lpa = lanes_per_agent(num_actions);
     e->lpr = sectors_per_row(num_actions);
     if (num_actions <= 32) {
-        // row block: [8*LPR floats of Q][8 words of writer info][spare inline entries], power-of-two sized
-        const int info_off = 8 * e->lpr;  // the writer info starts on a 32-byte sector
-        // agents cluster on the deterministic environments (a greedy policy sends everybody at s to the same s'),
-        // so rows with dozens of writers are common: the block is four times the Q row (A=16: 256 B, 44 inline
-        // writer entries; A<=8: 128 B, 20 entries); only longer lists spill to the per-agent overflow list
-        const int ld = 4 * info_off;
-        e->ld = ld;
-        e->T.info_off = info_off;
-        e->T.inline_cap = ld - info_off - 4 - 2;  // two words behind the inline entries hold the spill descriptor
+        // dense Q rows of whole 32-byte sectors; the writer lists of the list form (three times the row size per state:
+        // agents cluster on the deterministic environments, rows with dozens of writers are common) live in info[]
+        e->ld = 8 * e->lpr;
+        e->T.info_ld = 3 * e->ld;
+        e->T.inline_cap = e->T.info_ld - 4 - 2;  // two words behind the inline entries hold the spill descriptor
     } else {  // generic path (sequential learn kernel): plain padded rows, no writer info
         e->ld = ((num_actions + 3) / 4) * 4;
-        e->T.info_off = 0;
+        e->T.info_ld = 0;
         e->T.inline_cap = 0;
     }
     cudaDeviceProp prop;
@@ -201,7 +246,8 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
         while (bits < 31 && (1ll << bits) < e->S) ++bits;
         e->X.passes = (bits + kRadixBits - 1) / kRadixBits;
     }
-    e->strategy = getenv("QE_SORTED") ? atoi(getenv("QE_SORTED")) : 2;
+    e->strategy = getenv("QE_FORM") ? atoi(getenv("QE_FORM")) : (getenv("QE_SORTED") ? atoi(getenv("QE_SORTED")) : 3);
+    if (e->strategy < 0 || e->strategy > 3) e->strategy = 3;
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     e->T.spill_slots = 1024;
@@ -223,9 +269,11 @@ int qe_destroy(qe_engine_t* e) {
     for (int b = 0; b < 2; ++b) { cudaFree(e->X.key[b]); cudaFree(e->X.val[b]); }
     cudaFree(e->X.rank); cudaFree(e->X.targ); cudaFree(e->X.mhist); cudaFree(e->X.rrec); cudaFree(e->X.rmask); cudaFree(e->X.hmask); cudaFree(e->X.hrec);
     cudaFree(e->X.seg); cudaFree(e->X.rowtot); cudaFree(e->X.dbg);
+    for (int b = 0; b < 2; ++b) { cudaFree(e->P.rec[b]); cudaFree(e->P.pos[b]); cudaFree(e->P.kv[b]); cudaFree(e->P.seg[b]); }
+    cudaFree(e->P.ghist); cudaFree(e->P.rowtot); cudaFree(e->P.ctr);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1); cudaFree(e->X.ghist);
-    cudaFree(e->q_real); cudaFree(e->T.later_buf); cudaFree(e->T.spill); cudaFree(e->T.spill_next); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
+    cudaFree(e->q_real); cudaFree(e->info_real); cudaFree(e->T.later_buf); cudaFree(e->T.spill); cudaFree(e->T.spill_next); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
     cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta); cudaFree(e->stage); cudaFree(e->d_thresh); cudaFree(e->d_lr);
     delete e;
     return QE_OK;
@@ -239,12 +287,19 @@ int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
 int32_t qe_fused_form(qe_engine_t* e) { return e->current; }
 int qe_set_fused_form(qe_engine_t* e, int32_t form) {
     std::lock_guard<std::mutex> lk(e->mu);
-    if (form < 0 || form > 2) return fail(QE_ERR_ARG, "form must be 0 (writer lists), 1 (per-step sort) or 2 (pick by measurement)");
+    if (form < 0 || form > 3) return fail(QE_ERR_ARG, "form must be 0 (writer lists), 1 (per-step sort), 2 (pick between those two by measurement) or 3 (target pipeline)");
     e->strategy = form;
     return QE_OK;
 }
 int qe_debug_counters(qe_engine_t* e, uint64_t* out8_host, int32_t reset) {
     std::lock_guard<std::mutex> lk(e->mu);
+    if (e->current == 3 && e->P.ctr) {  // the pipelined form: ctr[8..15] of the last launch
+        unsigned int h[56];
+        CK(cudaMemcpy(h, e->P.ctr + 8, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 8; ++i) out8_host[i] = h[i];
+        if (reset == 2) for (int i = 8; i < 56; ++i) out8_host[i] = h[i];  // development: sort stage laps (56 values)
+        return QE_OK;
+    }
     if (!e->X.dbg) return fail(QE_ERR_ARG, "no counters");
     CK(cudaMemcpy(out8_host, e->X.dbg, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (reset) CK(cudaMemset(e->X.dbg, 0, 8 * sizeof(uint64_t)));
@@ -437,6 +492,7 @@ static int launch_learn_exact(qe_engine* e, const int32_t* s, const int32_t* a, 
     int blocks = 0;
     int rc = coop_blocks(e, learn_exact_kernel<LPR>, (long long)n, &blocks);
     if (rc) return rc;
+    if ((rc = ensure_info(e)) != QE_OK) return rc;
     uint32_t epoch = ++e->step;
     Table T = e->T;
     float gamma = e->gamma;
@@ -551,6 +607,7 @@ int qe_set_state_base(qe_engine_t* e, int64_t first_state) {
     if (first_state < 0) return fail(QE_ERR_ARG, "first_state must be >= 0");
     e->state_base = first_state;
     e->T.q = e->q_real - (size_t)first_state * (size_t)e->ld;  // never dereferenced outside [first_state, first_state + S)
+    if (e->info_real) e->T.info = e->info_real - (size_t)first_state * (size_t)e->T.info_ld;
     return QE_OK;
 }
 int qe_set_agent_ids(qe_engine_t* e, const uint32_t* ids) {
@@ -577,6 +634,7 @@ int qe_serve_bootstrap(qe_engine_t* e, const int32_t* rows, const int32_t* befor
     std::lock_guard<std::mutex> lk(e->mu);
     if (n <= 0) return QE_OK;
     if (e->A > 32) return fail(QE_ERR_ARG, "qe_serve_bootstrap supports at most 32 actions");
+    { int rc = ensure_info(e); if (rc) return rc; }
     serve_bootstrap_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->T, rows, before, mask_bits, out, n, e->step, use_versions);
     e->launches++;
     CK(cudaGetLastError());
@@ -680,9 +738,9 @@ constexpr int kProbeEvery = 12;
 static int pick_form(qe_engine* e, const FusedArgs& F, bool* time_it) {
     *time_it = false;
     if (e->state_base != 0 || e->A > 32 || !e->X.seg) return 0;
-    if (F.accumulate) return 0;  // the plain-atomics update lives in fused_kernel
+    if (F.accumulate || F.evaluate) return 0;  // the plain-atomics update and the evaluation loop live in fused_kernel
+    if (e->strategy == 3) return e->S < (1ll << 30) ? 3 : 1;  // the pipeline's records keep the state in 30 bits
     if (e->strategy == 0 || e->strategy == 1) return e->strategy;
-    if (F.evaluate) return e->current;
     if (e->timed_kind >= 0) {  // collect the launch timed last
         float ms = 0.0f;
         if (cudaEventSynchronize(e->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess && ms > 0.0f)
@@ -721,7 +779,17 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     bool timed = false;
     const int form = pick_form(e, F, &timed);
     if (timed) CK(cudaEventRecord(e->ev0, st));
-    if (form == 1) {
+    if (form == 3) {
+        int rc = coop_blocks(e, fused_pipe_kernel<ENV, LPR>, (long long)F.n, &blocks);
+        if (rc) return rc;
+        if ((rc = ensure_pipe(e, blocks)) != QE_OK) return rc;  // one sorting warp per block
+        e->P.parity0 = 0;
+        e->P.state_base = e->state_base;
+        CK(cudaMemsetAsync(e->P.ctr, 0, 64 * sizeof(unsigned int), st));
+        PipeScratch P = e->P;
+        void* args[] = {&T, &F, &P};
+        CK(cudaLaunchCooperativeKernel((void*)fused_pipe_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
+    } else if (form == 1) {
         int rc = coop_blocks(e, fused_sorted_kernel<ENV, LPR>, (long long)F.n, &blocks);
         if (rc) return rc;
         if (blocks > kSortMaxBlocks * kSortStride) blocks = kSortMaxBlocks * kSortStride;
@@ -742,6 +810,8 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     } else {
         int rc = coop_blocks(e, fused_kernel<ENV, LPR>, (long long)F.n, &blocks);
         if (rc) return rc;
+        if (!F.evaluate && (rc = ensure_info(e)) != QE_OK) return rc;
+        T = e->T;
         void* args[] = {&T, &F};
         CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
     }
@@ -750,7 +820,7 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
         e->timed_kind = form;
         e->timed_work = (double)F.n * (double)F.steps;
     }
-    e->current = form;
+    if (!F.evaluate) e->current = form;
     e->launches++;
     e->last_grid = blocks;
     return QE_OK;

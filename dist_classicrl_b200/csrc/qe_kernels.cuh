@@ -1,8 +1,9 @@
 // qe_kernels.cuh -- CUDA kernels of the engine (sm_100a): select, exact sequential TD update, env steps, fused loop.
 //
-// Table layout in HBM.  One *row block* per state: [Q row: 4*LPA floats][writer info: 8 words][spare inline entries],
-// padded to a power of two (A=16: 128 B = one L2 line; A=8: 64 B).  A row gather therefore brings the writer info
-// of that state along in the same line/DRAM page.
+// Table layout in HBM.  Q is dense: one row of 8*LPR floats per state (A=16: 64 B, so the 1M-state table of config 3
+// is 64 MB and lives in L2).  The writer lists of this file's exact update live in a SEPARATE array (`info`, three
+// times the row size per state, allocated the first time a writer-list kernel runs): round 1 kept them inside a
+// 256-byte row block, which made every row gather of every kernel stride over metadata only this form reads.
 //
 // Exact sequential TD update in parallel (DESIGN.md "TD update"):
 //   The reference applies agents 0..N-1 one after the other (QLO:806-817), so agent i must see every write of
@@ -41,11 +42,12 @@ constexpr int kErrInvalidMove = 1, kErrEmpty = 2, kErrTimeout = 4;
 constexpr uint64_t kTimeoutNs = 4000000000ull;  // a TD update that has not drained after 4 s is reported, not waited for
 
 struct Table {
-    float* q;          // [S][ld] row blocks
-    int ld;            // floats per row block (power of two)
+    float* q;          // [S][ld] dense Q rows
+    int ld;            // floats per row (8 * LPR: whole 32-byte sectors)
     int A;             // actions
-    int info_off;      // float offset of the writer info inside a row block
-    int inline_cap;    // writer entries stored inline in the row block (>= 4); the two words after them hold the spill descriptor
+    uint32_t* info;    // [S][info_ld] writer info of the writer-list form (nullptr until first used)
+    int info_ld;       // words per state in info[]
+    int inline_cap;    // writer entries stored inline in a state's info block (>= 4); the two words after them hold the spill descriptor
     uint32_t* spill;   // [spill_slots][kSpillCap] contiguous writer entries of crowded rows (beyond the inline ones)
     int spill_slots;
     int* spill_next;   // [2] slots handed out in this step (by epoch parity; the other one is reset meanwhile)
@@ -62,7 +64,7 @@ struct Table {
 // writer info words: [0] count, [1] epoch (one u64, atomics), [2] overflow head idx, [3] its epoch (one u64),
 //                    [4 .. 4+inline_cap) entries (agent24 | action << 24)
 __device__ __forceinline__ uint32_t* row_info(const Table& T, int s) {
-    return reinterpret_cast<uint32_t*>(T.q + (size_t)s * T.ld + T.info_off);
+    return T.info + (size_t)s * T.info_ld;
 }
 
 __device__ __forceinline__ uint64_t global_ns() {

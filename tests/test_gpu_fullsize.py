@@ -20,6 +20,7 @@ from oracle.envs import T_INIT  # noqa: E402
 
 EPS, LR, GAMMA, P_TERM = 0.1, 0.1, 0.99, 0.05
 TT = int(math.ceil(P_TERM * 2.0**32))
+_CACHE = {}
 
 
 @pytest.fixture(scope="module")
@@ -152,15 +153,15 @@ def test_config3_chunking_and_determinism(capi):
             x.close()
 
 
-@pytest.mark.parametrize("form", ["0", "1"])
-@pytest.mark.parametrize("S,A,N,steps", [(2000, 16, 50_000, 24), (97, 5, 4096, 16), (300_000, 8, 200_000, 10)])
-def test_both_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form, S, A, N, steps):
-    """QE_SORTED pins the form of the TD update (0 = writer lists, 1 = per-step sort); both must reproduce the
-    oracle bit for bit, also when hundreds of agents herd on one row."""
-    monkeypatch.setenv("QE_SORTED", form)
+@pytest.mark.parametrize("form", ["0", "1", "3"])
+@pytest.mark.parametrize("S,A,N,steps", [(2000, 16, 50_000, 24), (97, 5, 4096, 16), (300_000, 8, 200_000, 10), (3, 20, 1000, 6), (70_000, 32, 33, 40)])
+def test_all_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form, S, A, N, steps):
+    """QE_FORM pins the form of the TD update (0 = writer lists, 1 = per-step sort, 3 = target pipeline); all must
+    reproduce the oracle bit for bit, also when hundreds of agents herd on one row (or all of them on three rows)."""
+    monkeypatch.setenv("QE_FORM", form)
     seed = 9
     q_o, st_o, rew_o, _ = _oracle(S, A, N, steps, seed, 1)
-    assert np.bincount(st_o, minlength=S).max() > (40 if N > 10 * S else 1)
+    assert np.bincount(st_o, minlength=S).max() > (40 if N > 10 * S else 0)
     r = Run(capi, S, A, N, seed, 1)
     try:
         r.steps(steps // 2)
@@ -174,12 +175,13 @@ def test_both_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form
 
 
 def test_automatic_form_selection_switches_forms_and_stays_exact(capi, monkeypatch):
-    """Default strategy (no QE_SORTED): the engine's first four launches are {writer lists cold, timed, sort cold,
+    """Strategy 2 (QE_FORM=2; round 1's default): the engine's first four launches are {writer lists cold, timed, sort cold,
     timed}, then it keeps the faster form and times both again in two adjacent launches every 12 launches.  Whatever
     it picks, the results are the oracle's; qe_set_fused_form pins and releases the choice."""
     monkeypatch.delenv("QE_SORTED", raising=False)
+    monkeypatch.setenv("QE_FORM", "2")
     S, A, N, launches, k, seed = 4000, 16, 60_000, 32, 1, 4
-    q_o, st_o, rew_o, _ = _oracle(S, A, N, launches * k + 4, seed, 1)
+    q_o, st_o, rew_o, _ = _oracle(S, A, N, launches * k + 6, seed, 1)
     r = Run(capi, S, A, N, seed, 1)
     try:
         forms = []
@@ -197,8 +199,33 @@ def test_automatic_form_selection_switches_forms_and_stays_exact(capi, monkeypat
         capi.check(capi.lib().qe_set_fused_form(r.h, 1))
         r.steps(2)
         assert capi.lib().qe_fused_form(r.h) == 1
+        capi.check(capi.lib().qe_set_fused_form(r.h, 3))
+        r.steps(2)
+        assert capi.lib().qe_fused_form(r.h) == 3
         with pytest.raises(ValueError):
-            capi.check(capi.lib().qe_set_fused_form(r.h, 3))
+            capi.check(capi.lib().qe_set_fused_form(r.h, 4))
+        assert np.array_equal(r.states.cpu().numpy(), st_o)
+        assert np.array_equal(r.ep.cpu().numpy(), rew_o)
+        assert np.array_equal(r.table(), q_o)
+    finally:
+        r.close()
+
+
+@pytest.mark.parametrize("form", ["3", "1", "0"])
+def test_config3_long_run_every_form_vs_oracle(capi, monkeypatch, form):
+    """2^20 agents x 72 vector steps (the bench window and beyond; the agents herd: rows with dozens of writers),
+    every form of the exact update pinned, bit-exact against the C oracle."""
+    monkeypatch.setenv("QE_FORM", form)
+    S, A, N, steps, seed = 1_000_000, 16, 1 << 20, 72, 0
+    key = ("c3long", steps)
+    if key not in _CACHE:
+        _CACHE[key] = _oracle(S, A, N, steps, seed, 1)
+    q_o, st_o, rew_o, _ = _CACHE[key]
+    r = Run(capi, S, A, N, seed, 1)
+    try:
+        for k in (8, 8, 8, 8, 8, 8, 8, 8, 1, 7):
+            r.steps(k)
+        assert capi.lib().qe_fused_form(r.h) == int(form)
         assert np.array_equal(r.states.cpu().numpy(), st_o)
         assert np.array_equal(r.ep.cpu().numpy(), rew_o)
         assert np.array_equal(r.table(), q_o)
