@@ -55,7 +55,11 @@ struct qe_engine {
     uint32_t step = 0;       // global step counter (epoch / tag source)
     SortedScratch X{};       // scratch of the sorted fused loop (qe_sorted.cuh)
     PipeScratch P{};         // scratch of the pipelined fused loop (qe_pipe.cuh)
-    int pipe_sorters = 0;    // P.ghist was sized for this many sorting warps (one per block)
+    int pipe_sorters = 0;    // P.ghist was sized for this many blocks
+    bool pipe_valid = false; // P.pos / P.seg / P.kv hold the sort of pipe_states[0 .. pipe_n) as the last pipelined launch left them
+    const int32_t* pipe_states = nullptr;
+    int pipe_n = 0;
+    int pipe_sorted_n = 0;   // agents of the order P.kv / P.seg still describe (0: none; seg[] is all-empty then)
     int sorted_grid = 0;     // ghist was sized for this many blocks
     // The fused loop has two exact forms of the TD update: writer lists (qe_kernels.cuh; best while few agents share
     // a row) and the per-step sort (qe_sorted.cuh; best once agents herd).  Both give identical results, so the engine
@@ -116,16 +120,17 @@ static int ensure_agents(qe_engine* e, int n) {
     }
     {
         PipeScratch& P = e->P;
-        for (int b = 0; b < 2; ++b) {
-            cudaFree(P.rec[b]); cudaFree(P.pos[b]); cudaFree(P.kv[b]);
-            P.rec[b] = nullptr; P.pos[b] = nullptr; P.kv[b] = nullptr;
-        }
-        for (int b = 0; b < 2; ++b) {
-            CK(cudaMalloc(&P.rec[b], sizeof(uint4) * (size_t)cap));
-            CK(cudaMalloc(&P.pos[b], sizeof(int32_t) * cap));
-            CK(cudaMalloc(&P.kv[b], sizeof(int2) * (size_t)cap));
-            CK(cudaMemset(P.rec[b], 0xFF, sizeof(uint4) * (size_t)cap));
-        }
+        for (int b = 0; b < 2; ++b) { cudaFree(P.kv[b]); P.kv[b] = nullptr; }
+        cudaFree(P.tw); cudaFree(P.rec); cudaFree(P.pos);
+        P.tw = nullptr; P.rec = nullptr; P.pos = nullptr;
+        e->pipe_valid = false;
+        e->pipe_sorted_n = 0;  // the order kv[] described is gone with the buffers: seg[] starts from all-empty again
+        if (P.seg) CK(cudaMemset(P.seg, 0, sizeof(uint2) * (size_t)e->S));
+        CK(cudaMalloc(&P.tw, sizeof(uint4) * (size_t)cap));
+        CK(cudaMalloc(&P.rec, sizeof(uint2) * ((size_t)cap + 8)));  // phase T reads whole 32-byte groups
+        CK(cudaMalloc(&P.pos, sizeof(int32_t) * cap));
+        CK(cudaMemset(P.rec, 0xFF, sizeof(uint2) * ((size_t)cap + 8)));
+        for (int b = 0; b < 2; ++b) CK(cudaMalloc(&P.kv[b], sizeof(int2) * (size_t)cap));
     }
     e->cap = cap;
     return QE_OK;
@@ -133,11 +138,9 @@ static int ensure_agents(qe_engine* e, int n) {
 // state-indexed scratch of the pipelined form (segment bounds, two parities), allocated at its first launch
 static int ensure_pipe(qe_engine* e, int sorters) {
     PipeScratch& P = e->P;
-    if (!P.seg[0]) {
-        for (int b = 0; b < 2; ++b) {
-            CK(cudaMalloc(&P.seg[b], sizeof(uint2) * (size_t)e->S));
-            CK(cudaMemset(P.seg[b], 0, sizeof(uint2) * (size_t)e->S));
-        }
+    if (!P.seg) {
+        CK(cudaMalloc(&P.seg, sizeof(uint2) * (size_t)e->S));
+        CK(cudaMemset(P.seg, 0, sizeof(uint2) * (size_t)e->S));
         CK(cudaMalloc(&P.rowtot, sizeof(int) * kRadix));
         CK(cudaMalloc(&P.ctr, 64 * sizeof(unsigned int)));
         int bits = 1;
@@ -178,6 +181,10 @@ static int check_device_errors(qe_engine* e, cudaStream_t st) {
     CK(cudaStreamSynchronize(st));
     if (h) {
         CK(cudaMemsetAsync(e->T.err, 0, sizeof(int), st));
+        // the pipelined form's persistent order may be half-written: start it over
+        e->pipe_valid = false;
+        e->pipe_sorted_n = 0;
+        if (e->P.seg) CK(cudaMemsetAsync(e->P.seg, 0, sizeof(uint2) * (size_t)e->S, st));
         if (h & kErrInvalidMove) return fail(QE_ERR_INVALID_MOVE, "Invalid move.");
         if (h & kErrEmpty) return fail(QE_ERR_EMPTY, "empty candidate or bootstrap action set");
         return fail(QE_ERR_TIMEOUT, "TD-update dependency resolution timed out");
@@ -254,8 +261,8 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     CK(cudaMalloc(&e->T.spill, sizeof(uint32_t) * (size_t)e->T.spill_slots * kSpillCap));
     CK(cudaMalloc(&e->T.spill_next, 2 * sizeof(int)));
     CK(cudaMemset(e->T.spill_next, 0, 2 * sizeof(int)));
-    CK(cudaMalloc(&e->phase_ns, 33 * sizeof(uint64_t)));
-    CK(cudaMemset(e->phase_ns, 0, 33 * sizeof(uint64_t)));
+    CK(cudaMalloc(&e->phase_ns, 48 * sizeof(uint64_t)));
+    CK(cudaMemset(e->phase_ns, 0, 48 * sizeof(uint64_t)));
     int rc = ensure_agents(e, 1024);
     if (rc) { qe_destroy(e); return rc; }
     *out = e;
@@ -269,8 +276,9 @@ int qe_destroy(qe_engine_t* e) {
     for (int b = 0; b < 2; ++b) { cudaFree(e->X.key[b]); cudaFree(e->X.val[b]); }
     cudaFree(e->X.rank); cudaFree(e->X.targ); cudaFree(e->X.mhist); cudaFree(e->X.rrec); cudaFree(e->X.rmask); cudaFree(e->X.hmask); cudaFree(e->X.hrec);
     cudaFree(e->X.seg); cudaFree(e->X.rowtot); cudaFree(e->X.dbg);
-    for (int b = 0; b < 2; ++b) { cudaFree(e->P.rec[b]); cudaFree(e->P.pos[b]); cudaFree(e->P.kv[b]); cudaFree(e->P.seg[b]); }
-    cudaFree(e->P.ghist); cudaFree(e->P.rowtot); cudaFree(e->P.ctr);
+    for (int b = 0; b < 2; ++b) cudaFree(e->P.kv[b]);
+    cudaFree(e->P.rec); cudaFree(e->P.pos); cudaFree(e->P.seg);
+    cudaFree(e->P.ghist); cudaFree(e->P.rowtot); cudaFree(e->P.ctr); cudaFree(e->P.tw);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1); cudaFree(e->X.ghist);
     cudaFree(e->q_real); cudaFree(e->info_real); cudaFree(e->T.later_buf); cudaFree(e->T.spill); cudaFree(e->T.spill_next); cudaFree(e->T.err); cudaFree(e->tile_counter); cudaFree(e->phase_ns); cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask); cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p);
@@ -320,11 +328,12 @@ double qe_debug_gridsync_us(qe_engine_t* e, int32_t iters) {
 }
 int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap) {
     std::lock_guard<std::mutex> lk(e->mu);
-    uint64_t h[33];
+    uint64_t h[48];
     if (cudaSetDevice(e->device) != cudaSuccess || cudaMemcpy(h, e->phase_ns, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess)
         return fail(QE_ERR_CUDA, "cannot read the phase clock");
     const int m = 1 + 3 * e->phase_steps;
     for (int i = 0; i < m && i < cap; ++i) out_host[i] = h[i];
+    if (cap >= 48) for (int i = 32; i < 48; ++i) out_host[i] = h[i];  // pipelined form: end of the sort inside phase "B1" of step i - 32
     return m < cap ? m : cap;
 }
 
@@ -780,16 +789,31 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     const int form = pick_form(e, F, &timed);
     if (timed) CK(cudaEventRecord(e->ev0, st));
     if (form == 3) {
-        int rc = coop_blocks(e, fused_pipe_kernel<ENV, LPR>, (long long)F.n, &blocks);
+        const size_t smem = pipe_smem_bytes(LPR);
+        CK(cudaFuncSetAttribute(fused_pipe_kernel<ENV, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_pipe_kernel<ENV, LPR>, 256, smem));
+        if (per_sm < 1) return fail(QE_ERR_CUDA, "the pipelined kernel cannot be made resident");
+        {
+            const long long want = ((long long)F.n + 255) / 256, maxb = (long long)per_sm * e->sms;
+            blocks = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
+        }
+        int rc = ensure_pipe(e, blocks);
         if (rc) return rc;
-        if ((rc = ensure_pipe(e, blocks)) != QE_OK) return rc;  // one sorting warp per block
-        e->P.parity0 = 0;
+        if (blocks > 32 * kScanPerLane) return fail(QE_ERR_CUDA, "the pipelined kernel's sort supports at most %d blocks", 32 * kScanPerLane);
+        e->P.sorted_valid = (e->pipe_valid && e->pipe_states == F.st_a && e->pipe_n == F.n && !getenv("QE_PIPE_RESORT")) ? 1 : 0;
         e->P.state_base = e->state_base;
+        e->P.old_n = e->pipe_sorted_n;
         CK(cudaMemsetAsync(e->P.ctr, 0, 64 * sizeof(unsigned int), st));
         PipeScratch P = e->P;
         void* args[] = {&T, &F, &P};
-        CK(cudaLaunchCooperativeKernel((void*)fused_pipe_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
+        CK(cudaLaunchCooperativeKernel((void*)fused_pipe_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, smem, st));
+        e->pipe_valid = true;
+        e->pipe_states = F.st_a;
+        e->pipe_n = F.n;
+        e->pipe_sorted_n = F.n;
     } else if (form == 1) {
+        if (!F.evaluate) e->pipe_valid = false;
         int rc = coop_blocks(e, fused_sorted_kernel<ENV, LPR>, (long long)F.n, &blocks);
         if (rc) return rc;
         if (blocks > kSortMaxBlocks * kSortStride) blocks = kSortMaxBlocks * kSortStride;
@@ -803,11 +827,13 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
         void* args[] = {&T, &F, &X};
         CK(cudaLaunchCooperativeKernel((void*)fused_sorted_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, 0, st));
     } else if (F.accumulate) {
+        e->pipe_valid = false;
         int rc = coop_blocks(e, fused_kernel<ENV, LPR, true>, (long long)F.n, &blocks);
         if (rc) return rc;
         void* args[] = {&T, &F};
         CK(cudaLaunchCooperativeKernel((void*)fused_kernel<ENV, LPR, true>, dim3(blocks), dim3(256), args, 0, st));
     } else {
+        e->pipe_valid = false;  // (an evaluation run moves the agents too)
         int rc = coop_blocks(e, fused_kernel<ENV, LPR>, (long long)F.n, &blocks);
         if (rc) return rc;
         if (!F.evaluate && (rc = ensure_info(e)) != QE_OK) return rc;

@@ -14,22 +14,24 @@
 //      masked max and publishes its own target.  A chain of c writers of one cell costs nothing; only a cross-row
 //      read of a row with earlier writers is a dependency (26 levels instead of 56 on config 3, and flat later on).
 //      Same floating-point operations in the same order as the reference: the result is bit-identical.
-//   2. Dependencies always point to SMALLER agent indices.  Tiles of 32 agents are therefore claimed in increasing
-//      order by resident warps which simply poll: a predecessor was claimed earlier, so it is finished or running --
-//      no deferred records, no sweeps, no parking, one pass.  Most predecessors were processed long before their
-//      dependants are claimed, so most polls succeed at once; a chain costs one L2 round trip per level.
+//   2. Dependencies always point to SMALLER agent indices.  Chunks of 32 agents are claimed in increasing order by
+//      resident warps whose lanes simply poll: a predecessor was claimed earlier, so it is finished, in some lane, or
+//      next in line for a warp whose lanes all hold smaller agents -- the smallest unfinished agent always makes
+//      progress: no deferred records, no sweeps, no parking, one pass.  Most predecessors were processed long before
+//      their dependants come up, so most polls succeed at once; a chain costs one L2 round trip per level.
 //
 //   Writers whose next state is their own row (self loops: the attractors a greedy policy herds the agents into --
 //   one row of config 3 holds 1300 agents after 600 steps) would form a chain of one hop per agent; their targets are
 //   derived in line during the replay (the replayed row IS the row they bootstrap from), so they cost no hop at all.
 //
-// Per vector step (three grid barriers):
+// Per vector step:
 //   phase A   select + environment step (one lane per agent); every agent writes its writer record
 //             {agent, action, target or "pending", reward, state} at its position in the sort of the CURRENT states
-//   phase T   in-order target pipeline (above)            ||   phase S  warp 0 of every CTA sorts the NEXT states (known
-//             since the end of phase A) for the next step: stable LSD radix sort, 10-bit digits, one warp = one block
-//             of the sort (its scattered stores use the store path of all SMs, its instructions 1/8 of their issue slots)
+//   phase T   in-order target pipeline (above)
 //   phase C   commit: one pass over the sorted records replays every row's segment and stores the cells that changed
+//   phase S   stable LSD radix sort of the NEXT states (10-bit digits, all CTAs): positions and segment bounds per state
+//             for the next step.  The order survives the launch: the next launch only checks that the states are
+//             still the ones that were sorted.
 //
 // Requires the legal-action mask to be a function of the state (true for the device environments).
 #pragma once
@@ -47,32 +49,37 @@ constexpr uint64_t kPipeTimeoutNs = 3000000000ull;
 #endif
 
 struct PipeScratch {
-    uint4* rec[2];        // [cap] writer records by sorted position, by step parity:
-                          //   x = agent | action << 24, y = target bits or kPending, z = reward bits, w = state << 2 | term << 1 | self
-    uint2* seg[2];        // [S] per state {segment start, segment end} in rec[parity]; stale unless rec[start].w >> 2 == state
-    int32_t* pos[2];      // [cap] agent -> sorted position
+    uint2* rec;           // [cap + 8] writer records by sorted position: x = agent | action << 24 | self << 29, y = target bits or kPending
+    uint2* seg;           // [S] per state {segment start, segment end} in rec ({0, 0}: nobody stands on the state; the sort clears
+                          //     the bounds of the previous order before it writes the new ones)
+    int32_t* pos;         // [cap] agent -> sorted position
     int2* kv[2];          // [cap] radix ping-pong {key, agent}
-    int* ghist;           // [blocks][kRadix] digit counts per sorting warp, scanned in place
+    uint4* tw;            // [cap] per agent, from phase A to phase T: {next state, sorted position, reward bits, action | term << 7}
+    int* ghist;           // [kRadix][blocks] digit counts per block, scanned in place
     int* rowtot;          // [kRadix] digit totals
-    unsigned int* ctr;    // [64] 0,1: chunk claims by parity; 2: sorter barrier arrivals; 3: its generation; 4: abort flag
+    unsigned int* ctr;    // [64] 0: chunk claims of phase T; 4: abort flag; 6: "the states are not the sorted ones"; 8..: development counters
     int passes;           // radix passes for the state range
-    int parity0;          // parity of the first step of the launch
+    int sorted_valid;     // pos / seg / kv hold the sort of the states this launch starts from (to be checked)
+    int old_n;            // agents of the order kv[passes & 1] and seg[] still describe (0: none)
     int64_t state_base;   // keys are state - state_base (sharded tables)
 };
 
-__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
+// four 8-byte records with one 256-bit load (32-byte aligned; SASS LDG.E.ENL2.256.STRONG.GPU: one L1 wavefront per lane)
+__device__ __forceinline__ U8 ld_relaxed_v8(const uint2* p) {
+    U8 r;
+    asm volatile("ld.relaxed.gpu.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p) : "memory");
+    return r;
 }
 __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned int* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// 16 bytes global -> shared without passing through registers (L2 only: the source is rewritten between phases)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ int warp_incl_scan(int v) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -82,36 +89,8 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
     }
     return v;
 }
-
-// Barrier among the sorting warps (one per CTA; the other warps are busy with phase T).  Generation counter; all CTAs
-// are co-resident (cooperative launch).  Gives up when the abort flag is set (a timeout somewhere: the launch is void).
-__device__ __forceinline__ void sorter_barrier(unsigned int* ctr, int nb) {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-        const uint32_t gen = ld_acquire_u32(ctr + 3);
-        __threadfence();
-        if (atomicAdd(ctr + 2, 1u) == (unsigned int)(nb - 1)) {
-            atomicExch(ctr + 2, 0u);
-            __threadfence();
-            atomicAdd(ctr + 3, 1u);
-        } else {
-            const uint64_t t0 = global_ns();
-            uint32_t spins = 0;
-            while (ld_acquire_u32(ctr + 3) == gen) {
-                __nanosleep(100);
-                if ((++spins & 1023u) == 0u && (ld_relaxed_u32(ctr + 4) != 0u || global_ns() - t0 > kPipeTimeoutNs)) {
-                    atomicExch(ctr + 4, 1u);
-                    break;
-                }
-            }
-        }
-        __threadfence();
-    }
-    __syncwarp();
-}
-
-// lanes of the warp whose 10-bit digit equals this lane's (idle lanes pass d >= kRadix and match nobody that matters).
-// match.any costs one hardware iteration per distinct value (~32 here); ten ballots are several times cheaper.
+// lanes of the warp whose 10-bit digit equals this lane's.  match.any costs one hardware iteration per distinct value
+// (~32 here); ten ballots are several times cheaper.
 __device__ __forceinline__ uint32_t digit_peers(uint32_t d, bool act) {
     uint32_t peers = __ballot_sync(kFull, act);
 #pragma unroll
@@ -123,26 +102,39 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d, bool act) {
     return peers;
 }
 
-// Stable LSD radix sort of the agents by state, run by ONE WARP PER CTA (b = blockIdx.x of nb = gridDim.x): warp b owns
-// the contiguous chunk [lo, hi) of the input of every pass.  Per pass: digit histogram of the chunk (shared memory) ->
-// ghist[b][.]; barrier; exclusive scan of every digit's column over the warps (digits dealt round-robin to the warps);
-// barrier; first free position per digit = digit base + warps before; the chunk is walked in order, 32 keys at a
-// time, position = that + earlier lanes with the same digit; barrier.  Keys and agents travel as one 8-byte pair.  The
-// last pass also writes pos[agent]; then every run of equal keys gets its bounds in seg[].  One warp has no latency
-// hiding of its own: every stage issues its loads in batches before it consumes them.
-__device__ __forceinline__ void pipe_sort_warp(int* hist, const int32_t* states, int n, int par, const PipeScratch& X, int b, int nb, int stat_slot = 16) {
-    const int lane = threadIdx.x & 31;
-#ifdef QE_PIPE_STATS  // ctr[stat_slot + 8 * pass + stage] = latest time (ns since this warp entered the sort) any warp finished the stage
-    const uint64_t t_sort0 = global_ns();
-#define PIPE_LAP(stage) do { if (lane == 0 && ps < 2) atomicMax(X.ctr + stat_slot + 8 * ps + (stage), (unsigned int)(global_ns() - t_sort0)); } while (0)
-#else
-#define PIPE_LAP(stage) ((void)0)
-#endif
-    (void)stat_slot;
-    const int chunk = ((n + nb - 1) / nb + 31) & ~31;
-    const int lo = min(b * chunk, n), hi = min(lo + chunk, n);
+// Stable LSD radix sort of the agents by state, all CTAs.  Block b owns the contiguous chunk [b * chunk, ...) of the
+// input of every pass, warp w of the block a contiguous part of it.  Per pass: per-warp digit histograms (shared
+// memory) -> block counts ghist[digit][block]; grid barrier; exclusive scan of every digit's row over the blocks (one
+// warp per digit, every lane a contiguous piece of the row); grid barrier; first free position per (digit, warp) =
+// digit base + blocks before + warps before; the part is walked in order, 32 keys at a time, position = that + earlier
+// lanes with the same digit; grid barrier.  Keys and agents travel as one 8-byte pair.  The last pass also writes
+// pos[agent].  Returns the buffer that holds the sorted pairs; pipe_bounds() then gives every run of equal keys its
+// bounds in seg[] (no barrier in between is needed by the caller's next phase unless it reads seg[]).
+constexpr int kScanPerLane = 20;  // the column scan keeps ceil(blocks / 32) counts per lane in registers: up to 640 blocks
+template <int WARPS>
+__device__ __forceinline__ int pipe_sort(cg::grid_group& grid, int (*whist)[kRadix], int* s_base, int* s_wsum, const int32_t* states, int n,
+                                         int old_n, const PipeScratch& X) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x, nb = gridDim.x;
+    if (old_n > 0) {  // the previous order is still in kv[passes & 1] (nothing writes it before two barriers from here): reset its bounds
+        const int2* old = X.kv[X.passes & 1];
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < old_n; q += gridDim.x * blockDim.x) {
+            const int32_t kq = __ldcg(&old[q].x);
+            if (q == 0 || __ldcg(&old[q - 1].x) != kq) X.seg[kq] = make_uint2(0u, 0u);
+        }
+    }
+    const int chunk = ((n + nb - 1) / nb + 31) & ~31;          // per block, multiple of 32
+    const int part = ((chunk / 32 + WARPS - 1) / WARPS) * 32;  // per warp, multiple of 32
+    const int lo = min(b * chunk + warp * part, n), hi = min(min(b * chunk + (warp + 1) * part, (b + 1) * chunk), n);
     const int32_t bias = (int32_t)X.state_base;
+    int32_t* posout = X.pos;
     int src = 0;
+#ifdef QE_PIPE_STATS  // ctr[16 + 8 * pass + stage] += ns block 0 spent up to the end of the stage (since the previous lap)
+    uint64_t t_lap = global_ns();
+#define PIPE_LAP(ps, stage) do { if (b == 0 && threadIdx.x == 0 && (ps) < 3) { const uint64_t t_ = global_ns(); atomicAdd(X.ctr + 16 + 8 * (ps) + (stage), (unsigned int)(t_ - t_lap)); t_lap = t_; } } while (0)
+#else
+#define PIPE_LAP(ps, stage) ((void)0)
+#endif
     for (int ps = 0; ps < X.passes; ++ps) {
         const bool first = ps == 0, last = ps == X.passes - 1;
         const int shift = ps * kRadixBits;
@@ -156,112 +148,134 @@ __device__ __forceinline__ void pipe_sort_warp(int* hist, const int32_t* states,
             }
             return e;
         };
-        for (int d = lane; d < kRadix; d += 32) hist[d] = 0;
+        for (int d = lane; d < kRadix; d += 32) whist[warp][d] = 0;
         __syncwarp();
         for (int base = lo; base < hi; base += 256) {  // eight loads in flight per lane
-            int32_t kk[8];
+            int2 e[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int x = base + 32 * u + lane;
-                kk[u] = x < hi ? (first ? __ldcg(states + x) - bias : __ldcg(&in[x].x)) : 0;
-            }
+            for (int u = 0; u < 8; ++u) e[u] = load_pair(base + 32 * u + lane);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (base + 32 * u + lane < hi) atomicAdd(&hist[((uint32_t)kk[u] >> shift) & (kRadix - 1)], 1);
+                if (base + 32 * u + lane < hi) atomicAdd(&whist[warp][((uint32_t)e[u].x >> shift) & (kRadix - 1)], 1);
         }
-        __syncwarp();
-        int* mine = X.ghist + (size_t)b * kRadix;
-        for (int d = lane; d < kRadix; d += 32) mine[d] = hist[d];
-        PIPE_LAP(0);
-        sorter_barrier(X.ctr, nb);
-        PIPE_LAP(1);
-        for (int d = b; d < kRadix; d += nb) {  // exclusive scan of digit d's column over the warps
-            int carry = 0;
-            for (int x0 = 0; x0 < nb; x0 += 256) {
-                int v[8];
+        __syncthreads();
+        for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+            int t = 0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int x = x0 + 32 * u + lane;
-                    v[u] = x < nb ? __ldcg(X.ghist + (size_t)x * kRadix + d) : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int x = x0 + 32 * u + lane;
-                    const int incl = warp_incl_scan(v[u]);
-                    if (x < nb) X.ghist[(size_t)x * kRadix + d] = carry + incl - v[u];
-                    carry += __shfl_sync(kFull, incl, 31);
-                }
-            }
-            if (lane == 0) X.rowtot[d] = carry;
+            for (int w = 0; w < WARPS; ++w) t += whist[w][d];
+            X.ghist[(size_t)d * nb + b] = t;
         }
-        PIPE_LAP(2);
-        sorter_barrier(X.ctr, nb);
-        PIPE_LAP(3);
-        {   // first free position per digit for this warp
-            int carry = 0;
-            for (int d0 = 0; d0 < kRadix; d0 += 256) {
-                int v[8], w[8];
+        PIPE_LAP(ps, 0);
+        grid.sync();
+        PIPE_LAP(ps, 1);
+        {   // exclusive scan of every digit's row of block counts; one warp per digit, lane l owns entries [l * per, (l + 1) * per)
+            const int gw = b * WARPS + warp, nw = nb * WARPS;
+            const int per = (nb + 31) / 32;
+            for (int d = gw; d < kRadix; d += nw) {
+                int* row = X.ghist + (size_t)d * nb;
+                int v[kScanPerLane];
+                int sum = 0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    v[u] = __ldcg(X.rowtot + d0 + 32 * u + lane);
-                    w[u] = __ldcg(mine + d0 + 32 * u + lane);
+                for (int j = 0; j < kScanPerLane; ++j) {
+                    const int x = lane * per + j;
+                    v[j] = (j < per && x < nb) ? __ldcg(row + x) : 0;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int incl = warp_incl_scan(v[u]);
-                    hist[d0 + 32 * u + lane] = carry + incl - v[u] + w[u];
-                    carry += __shfl_sync(kFull, incl, 31);
+                for (int j = 0; j < kScanPerLane; ++j) sum += v[j];
+                const int incl = warp_incl_scan(sum);
+                int run = incl - sum;
+#pragma unroll
+                for (int j = 0; j < kScanPerLane; ++j) {
+                    const int x = lane * per + j;
+                    if (j < per && x < nb) row[x] = run;
+                    run += v[j];
                 }
+                if (lane == 31) X.rowtot[d] = incl;
             }
         }
-        __syncwarp();
-        PIPE_LAP(4);
-        int2 e[4], en[4];
+        PIPE_LAP(ps, 2);
+        grid.sync();
+        PIPE_LAP(ps, 3);
+        {   // digit bases (every block redoes the scan of the digit totals), then this warp's first free position per digit
+            static_assert(kRadix == 4 * 256, "four digits per thread");
+            const int4 v4 = __ldcg(reinterpret_cast<const int4*>(X.rowtot) + threadIdx.x);
+            const int v[4] = {v4.x, v4.y, v4.z, v4.w};
+            const int sum = v4.x + v4.y + v4.z + v4.w;
+            const int incl = warp_incl_scan(sum);
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int before = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) en[u] = load_pair(lo + 32 * u + lane);
-        for (int base = lo; base < hi; base += 128) {
+            for (int w = 0; w < WARPS; ++w) before += (w < warp) ? s_wsum[w] : 0;
+            int run = before + incl - sum;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { e[u] = en[u]; en[u] = load_pair(base + 128 + 32 * u + lane); }  // the next batch travels under this one
+            for (int j = 0; j < 4; ++j) { s_base[threadIdx.x * 4 + j] = run; run += v[j]; }
+        }
+        __syncthreads();
+        for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+            int run = s_base[d] + __ldcg(X.ghist + (size_t)d * nb + b);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int w = 0; w < WARPS; ++w) {
+                const int c = whist[w][d];
+                whist[w][d] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        PIPE_LAP(ps, 4);
+        for (int base = lo; base < hi; base += 256) {
+            int2 e[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) e[u] = load_pair(base + 32 * u + lane);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
                 const int x = base + 32 * u + lane;
                 const bool act = x < hi;
                 const uint32_t d = ((uint32_t)e[u].x >> shift) & (kRadix - 1);
                 const uint32_t peers = digit_peers(d, act);
                 if (act) {
-                    const int p = hist[d] + __popc(peers & ((1u << lane) - 1u));
+                    const int p = whist[warp][d] + __popc(peers & ((1u << lane) - 1u));
                     out[p] = e[u];
-                    if (last) X.pos[par][e[u].y] = p;
+                    if (last) posout[e[u].y] = p;
                 }
                 __syncwarp();
-                if (act && lane == (__ffs(peers) - 1)) hist[d] += __popc(peers);
+                if (act && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
                 __syncwarp();
             }
         }
-        PIPE_LAP(5);
-        sorter_barrier(X.ctr, nb);
-        PIPE_LAP(6);
+        PIPE_LAP(ps, 5);
+        grid.sync();
+        PIPE_LAP(ps, 6);
         src ^= 1;
     }
-    // segment bounds: the first and the last position of every run of equal keys (neighbours by shuffle, 256 positions per batch)
-    const int2* sorted = X.kv[src];
-    uint2* seg = X.seg[par];
-    for (int base = lo; base < hi; base += 256) {
-        int32_t kk[8];
+    return src;
+}
+// segment bounds: the first and the last position of every run of equal keys (neighbours by shuffle, 320 positions per batch)
+template <int WARPS>
+__device__ __forceinline__ void pipe_bounds(const int2* sorted, int n, const PipeScratch& X) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x, nb = gridDim.x;
+    const int chunk = ((n + nb - 1) / nb + 31) & ~31;
+    const int part = ((chunk / 32 + WARPS - 1) / WARPS) * 32;
+    const int lo = min(b * chunk + warp * part, n), hi = min(min(b * chunk + (warp + 1) * part, (b + 1) * chunk), n);
+    uint2* seg = X.seg;
+    constexpr int U = 10;
+    for (int base = lo; base < hi; base += 32 * U) {
+        int32_t kk[U];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int x = base + 32 * u + lane;
             kk[u] = x < n ? __ldcg(&sorted[x].x) : -1;
         }
         const int32_t left = base > 0 ? __ldcg(&sorted[base - 1].x) : -1;
-        const int32_t right = base + 256 < n ? __ldcg(&sorted[base + 256].x) : -1;
+        const int32_t right = base + 32 * U < n ? __ldcg(&sorted[base + 32 * U].x) : -1;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int x = base + 32 * u + lane;
             int32_t prev = __shfl_up_sync(kFull, kk[u], 1), next = __shfl_down_sync(kFull, kk[u], 1);
-            const int32_t pl = __shfl_sync(kFull, kk[u > 0 ? u - 1 : 0], 31), nf = __shfl_sync(kFull, kk[u < 7 ? u + 1 : 7], 0);
+            const int32_t pl = __shfl_sync(kFull, kk[u > 0 ? u - 1 : 0], 31), nf = __shfl_sync(kFull, kk[u < U - 1 ? u + 1 : U - 1], 0);
             if (lane == 0) prev = u > 0 ? pl : left;
-            if (lane == 31) next = u < 7 ? nf : right;
+            if (lane == 31) next = u < U - 1 ? nf : right;
             if (x < hi) {
                 if (prev != kk[u]) seg[kk[u]].x = (uint32_t)x;
                 if (next != kk[u]) seg[kk[u]].y = (uint32_t)(x + 1);
@@ -270,21 +284,32 @@ __device__ __forceinline__ void pipe_sort_warp(int* hist, const int32_t* states,
     }
 }
 
+// dynamic shared memory of fused_pipe_kernel<ENV, LPR>: the largest of the three phase layouts (see the kernel)
+__host__ __device__ constexpr size_t pipe_smem_bytes(int lpr) {
+    const size_t t = (size_t)(8 * lpr + 4) * 256, c = (size_t)(8 * lpr + 1) * 256, s = 8 * (size_t)kRadix + kRadix;
+    return sizeof(float) * (t > s ? (t > c ? t : c) : (s > c ? s : c));
+}
 #ifndef QE_PIPE_MIN_BLOCKS
-#define QE_PIPE_MIN_BLOCKS 4
+#define QE_PIPE_MIN_BLOCKS 3
 #endif
 template <int ENV, int LPR>
 __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Table T, FusedArgs F, PipeScratch X) {
     cg::grid_group grid = cg::this_grid();
+    constexpr int WARPS = 8;
     constexpr int RS = 8 * LPR + 4;                   // words per replayed row in phase T (one row per thread, 16-byte aligned, conflict-free)
-    constexpr int kRowWordsT = RS * 256;
-    constexpr int kRowWordsC = (8 * LPR + 1) * 256;   // phase C: one column per thread + the mask of cells it changed
+    constexpr int kWordsT = RS * 256;
+    constexpr int kWordsC = (8 * LPR + 1) * 256;      // phase C: one column per thread + the mask of cells it changed
+    constexpr int kWordsS = WARPS * kRadix + kRadix;  // phase S: per-warp digit counters + digit bases
+    constexpr int kWords = kWordsT > kWordsS ? (kWordsT > kWordsC ? kWordsT : kWordsC) : (kWordsS > kWordsC ? kWordsS : kWordsC);
     __shared__ double s_sum[8];
     __shared__ unsigned int s_cnt[8];
-    __shared__ __align__(16) float s_rows[kRowWordsT > kRowWordsC ? kRowWordsT : kRowWordsC];
-    __shared__ int s_hist[kRadix];
-    float* s_row = s_rows;                                                      // phase C: [8*LPR][256]
-    uint32_t* s_touch = reinterpret_cast<uint32_t*>(s_rows) + 8 * LPR * 256;    // phase C: [256]
+    __shared__ int s_wsum[WARPS];
+    extern __shared__ __align__(16) float s_mem[];  // pipe_smem_bytes(LPR) of dynamic shared memory
+    static_assert(kWords * sizeof(float) == pipe_smem_bytes(LPR), "host and device disagree about the shared memory size");
+    int (*s_whist)[kRadix] = reinterpret_cast<int (*)[kRadix]>(s_mem);
+    int* s_base = reinterpret_cast<int*>(s_mem) + WARPS * kRadix;
+    float* s_row = s_mem;                                                     // phase C: [8*LPR][256]
+    uint32_t* s_touch = reinterpret_cast<uint32_t*>(s_mem) + 8 * LPR * 256;   // phase C: [256]
     const int lane = threadIdx.x & 31;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
@@ -294,86 +319,106 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
     const int gwarp = tid >> 5, nwarps = nthreads >> 5;
     const bool clk = F.phase_ns != nullptr && tid == 0;
     const int wbase = threadIdx.x & ~31;  // first thread of this warp inside the block
-    const bool sorter = threadIdx.x < 32; // warp 0 of every CTA sorts
+    const int32_t sbase = (int32_t)X.state_base;
+    uint2* rec = X.rec;
+    const int32_t* pos = X.pos;
+    int old_n = X.old_n;
     if (clk) F.phase_ns[0] = global_ns();
 
-    // the sort of the current states (steady state: done during the previous step's phase T)
-    if (sorter) pipe_sort_warp(s_hist, F.st_a, n, X.parity0, X, blockIdx.x, gridDim.x);
-    grid.sync();
+    // ---------------- the order of the states this launch starts from: left behind by the previous launch (checked:
+    // every agent must sit at its recorded position with its current state), else sorted now
+    {
+        const int2* sorted = X.kv[X.passes & 1];
+        bool bad = !X.sorted_valid;
+        if (!bad)
+            for (int i = tid; i < n; i += nthreads) {
+                const uint32_t q = (uint32_t)__ldcg(pos + i);
+                if (q >= (uint32_t)n) { bad = true; continue; }
+                const int2 e = __ldcg(sorted + q);
+                bad |= e.y != i || e.x != __ldcg(F.st_a + i) - sbase;
+            }
+        if (__syncthreads_or(bad) && threadIdx.x == 0) atomicExch(X.ctr + 6, 1u);
+        grid.sync();
+        if (ld_relaxed_u32(X.ctr + 6) != 0u) {  // (the same answer in every block)
+            const int src = pipe_sort<WARPS>(grid, s_whist, s_base, s_wsum, F.st_a, n, old_n, X);
+            pipe_bounds<WARPS>(X.kv[src], n, X);
+            grid.sync();
+        }
+        old_n = n;
+    }
+    const int2* sorted = X.kv[X.passes & 1];  // {state - state_base, agent} by position, for the current step
 
     for (int k = 0; k < F.steps; ++k) {
-        const int par = (X.parity0 + k) & 1;
         int32_t* cur = (k & 1) ? F.st_b : F.st_a;
         int32_t* nxt = (k & 1) ? F.st_a : F.st_b;
         Uniforms U{F.uniforms ? F.uniforms + (size_t)k * n * F.slots : nullptr, F.slots, F.stream_seed, F.t0 + (uint32_t)k, F.agent0,
                    F.env_stream_seed, F.env_t0 + (uint32_t)k};
         const uint64_t thresh = F.eps_thresh[k];
         const float lr = F.lr[k];
-        uint4* rec = X.rec[par];
-        const int32_t* pos = X.pos[par];
         double loc_sum = 0.0;
         unsigned int loc_cnt = 0;
 
-        // ---------------- phase A: select + environment step; every agent files its writer record
-        for (int base = (tid & ~31); base < n; base += nthreads) {
-            const int i = base + lane;
-            const bool active = i < n;
-            int s = 0, mypos = 0;
-            uint32_t ew = 0u, valid = 0u, bits1 = 0u;
-            bool explore = false;
-            if (active) {
-                s = cur[i];
-                mypos = pos[i];
-                if (ENV != 0) ew = F.envw[i];
-                valid = F.use_masks ? env_mask<ENV>(s, ew, T.A, F.env_seed) : full;
-                explore = (uint64_t)U.draw(i, 0) < thresh;
-                bits1 = U.draw(i, 1);
-            }
-            RowGather<LPR> rows;
-            rows.issue(T, s, active);
-            float mx;
-            uint32_t tie;
-            rows.row_max_tie(valid, mx, tie);
-            int a = pick_action(T.A, valid, tie, explore, F.empty_all != 0, bits1);
-            if (active && a < 0) { atomicOr(T.err, kErrEmpty); a = 0; }
-            a = max(a, 0);
-            if (active) {
-                int32_t s2 = s;
-                float r = 0.0f;
-                bool term = false;
-                if (ENV == 0) mdp_step(s2, a, (uint32_t)F.S, T.A, F.env_seed, F.term_thresh, U.draw(i, 2), U.draw(i, 3), r, term);
-                else if (ENV == 1) {
-                    if (!ttt_step(ew, a, U.draw(i, 2), U.draw(i, 3), U.draw(i, 4), r, term)) atomicOr(T.err, kErrInvalidMove);
-                    s2 = ttt_state(ew & 0x3FFFFu);
-                } else {
-                    r = (float)a;
-                    ew += 1u;
-                    term = ew >= F.episode_len;
-                    if (term) ew = 0u;
-                    s2 = 0;
+        // ---------------- phase A: select + environment step; every agent files its writer record.  (The state and the
+        // position of the next tile are fetched while this one is processed.)
+        {
+            int base = tid & ~31;
+            int s_nx = 0, pos_nx = 0;
+            if (base + lane < n) { s_nx = cur[base + lane]; pos_nx = pos[base + lane]; }
+            for (; base < n; base += nthreads) {
+                const int i = base + lane;
+                const bool active = i < n;
+                const int s = s_nx, mypos = pos_nx;
+                if (base + nthreads + lane < n) { s_nx = cur[base + nthreads + lane]; pos_nx = pos[base + nthreads + lane]; }
+                uint32_t ew = 0u, valid = 0u, bits1 = 0u;
+                bool explore = false;
+                if (active) {
+                    if (ENV != 0) ew = F.envw[i];
+                    valid = F.use_masks ? env_mask<ENV>(s, ew, T.A, F.env_seed) : full;
+                    explore = (uint64_t)U.draw(i, 0) < thresh;
+                    bits1 = U.draw(i, 1);
                 }
-                nxt[i] = s2;
-                if (ENV != 0) F.envw[i] = ew;
-                F.tr_a[i] = (uint8_t)(a | (term ? 0x80 : 0));
-                F.tr_r[i] = r;
-                {
-                    // a terminated agent bootstraps from nothing: its target is known here (QLO:760-766)
-                    const uint32_t tg = term ? __float_as_uint(td_target_s(r, 0.0f, F.gamma)) : kPending;
-                    const uint32_t fl = ((uint32_t)s << 2) | (term ? 2u : 0u) | ((!term && s2 == s) ? 1u : 0u);
-                    rec[mypos] = make_uint4((uint32_t)i | ((uint32_t)a << 24), tg, __float_as_uint(r), fl);
+                RowGather<LPR> rows;
+                rows.issue(T, s, active);
+                float mx;
+                uint32_t tie;
+                rows.row_max_tie(valid, mx, tie);
+                int a = pick_action(T.A, valid, tie, explore, F.empty_all != 0, bits1);
+                if (active && a < 0) { atomicOr(T.err, kErrEmpty); a = 0; }
+                a = max(a, 0);
+                if (active) {
+                    int32_t s2 = s;
+                    float r = 0.0f;
+                    bool term = false;
+                    if (ENV == 0) mdp_step(s2, a, (uint32_t)F.S, T.A, F.env_seed, F.term_thresh, U.draw(i, 2), U.draw(i, 3), r, term);
+                    else if (ENV == 1) {
+                        if (!ttt_step(ew, a, U.draw(i, 2), U.draw(i, 3), U.draw(i, 4), r, term)) atomicOr(T.err, kErrInvalidMove);
+                        s2 = ttt_state(ew & 0x3FFFFu);
+                    } else {
+                        r = (float)a;
+                        ew += 1u;
+                        term = ew >= F.episode_len;
+                        if (term) ew = 0u;
+                        s2 = 0;
+                    }
+                    nxt[i] = s2;
+                    if (ENV != 0) F.envw[i] = ew;
+                    X.tw[i] = make_uint4((uint32_t)s2, (uint32_t)mypos, __float_as_uint(r), (uint32_t)a | (term ? 0x80u : 0u));
+                    // a terminated agent bootstraps from nothing: its target is known here (QLO:760-766); bit 29: self loop
+                    rec[mypos] = make_uint2((uint32_t)i | ((uint32_t)a << 24) | ((!term && s2 == s) ? (1u << 29) : 0u),
+                                            term ? __float_as_uint(td_target_s(r, 0.0f, F.gamma)) : kPending);
+                    float acc = F.ep_ret[i] + r;
+                    float fin = __int_as_float(0x7FC00000);
+                    if (term) { fin = acc; loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
+                    F.ep_ret[i] = acc;
+                    const size_t o = (size_t)k * n + i;
+                    if (F.trace_actions) F.trace_actions[o] = a;
+                    if (F.trace_rewards) F.trace_rewards[o] = r;
+                    if (F.trace_term) F.trace_term[o] = term;
+                    if (F.trace_next) F.trace_next[o] = s2;
+                    if (F.trace_epret) F.trace_epret[o] = fin;
                 }
-                float acc = F.ep_ret[i] + r;
-                float fin = __int_as_float(0x7FC00000);
-                if (term) { fin = acc; loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
-                F.ep_ret[i] = acc;
-                const size_t o = (size_t)k * n + i;
-                if (F.trace_actions) F.trace_actions[o] = a;
-                if (F.trace_rewards) F.trace_rewards[o] = r;
-                if (F.trace_term) F.trace_term[o] = term;
-                if (F.trace_next) F.trace_next[o] = s2;
-                if (F.trace_epret) F.trace_epret[o] = fin;
+                __syncwarp();
             }
-            __syncwarp();
         }
         if (F.ep_count) {
             for (int d = 16; d > 0; d >>= 1) {
@@ -390,16 +435,9 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
             }
             __syncthreads();
         }
+        if (tid == 0) X.ctr[0] = 0u;  // phase T's chunk counter (idle since the last barrier of the previous step)
         grid.sync();
         if (clk && k < 10) F.phase_ns[1 + 3 * k] = global_ns();
-
-        // ---------------- phase S (warp 0 of every CTA): the next step's sort, hidden under phase T
-        if (sorter && k + 1 < F.steps) {
-            const uint64_t ts0 = global_ns();
-            pipe_sort_warp(s_hist, nxt, n, par ^ 1, X, blockIdx.x, gridDim.x, 32);
-            if (blockIdx.x == 0 && lane == 0) PIPE_STAT(10, (global_ns() - ts0));  // ns spent sorting
-            (void)ts0;
-        }
 
         // ---------------- phase T: in-order target pipeline.  Chunks of 32 consecutive agents are claimed in increasing
         // order; a lane keeps its agent until the target is published and then takes the next agent of the warp's current
@@ -407,29 +445,28 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
         // (their per-agent words arrive while the lanes work); every pass of the loop polls up to four records per lane.
         // The replayed row lives in shared memory with its illegal cells at -inf, so the masked max is a plain max.
         {
-            unsigned int* claim = X.ctr + par;
-            const uint2* seg = X.seg[par] - X.state_base;
-            float* myrow = s_rows + threadIdx.x * RS;
+            unsigned int* claim = X.ctr;
+            const uint2* seg = X.seg - sbase;
+            float* myrow = s_mem + threadIdx.x * RS;
             auto claim_chunk = [&]() {
                 int c = 0;
                 if (lane == 0) c = (int)atomicAdd(claim, 1u);
                 return __shfl_sync(kFull, c, 0) * 32;
             };
-            struct Pend { int y, pos; float r; uint32_t at; };  // per-agent words of a chunk: lane L holds agent (base + L)
+            // per-agent words of a chunk ({s', position, reward, action | term << 7}): lane L holds agent (base + L)
             auto load_chunk = [&](int base) {
-                Pend q;
-                const int j = base + lane < n ? base + lane : 0;
-                q.y = nxt[j]; q.pos = pos[j]; q.r = F.tr_r[j]; q.at = F.tr_a[j];
+                uint4 q = make_uint4(0u, 0u, 0u, 0x80u);
+                if (base + lane < n) q = __ldcg(X.tw + base + lane);
                 return q;
             };
             int cb = claim_chunk(), cbn = claim_chunk(), cbnn = claim_chunk();
-            Pend pd = load_chunk(cb), pdn = load_chunk(cbn);
+            uint4 pd = load_chunk(cb), pdn = load_chunk(cbn);
             int pn = 0;  // agents of the current chunk handed out so far
             int i = 0, y = 0, mypos = 0;
             float r = 0.0f;
             uint32_t m2 = 0u, p = 0u, pe = 0u;
-            bool busy = false, first = false;
-            uint32_t waits = 0;
+            bool busy = false;
+            uint32_t waits = 0, spins_total = 0;
             auto row_max = [&]() {
                 float m = -INFINITY;
 #pragma unroll
@@ -440,7 +477,7 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
                 return m;
             };
             auto replay = [&](uint32_t ex, uint32_t tb) {
-                const uint32_t a2 = ex >> 24;
+                const uint32_t a2 = (ex >> 24) & 31u;
                 if ((m2 >> a2) & 1u) {  // an illegal cell stays at -inf: it cannot be the masked max
                     float* cell = myrow + a2;
                     *cell = td_from_target_s(*cell, __uint_as_float(tb), lr);
@@ -448,6 +485,7 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
             };
             const uint64_t t_start = global_ns();
             for (uint32_t spins = 0;; ++spins) {
+                spins_total = spins;
                 // ---- hand the next agents of the chunk to the free lanes (in batches: the refill path is divergent code);
                 // their row and segment bounds are fetched now and consumed at the end of this pass
                 const uint32_t freeb = __ballot_sync(kFull, !busy);
@@ -457,11 +495,10 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
                 if (cb < n && (__popc(freeb) >= 8 || (freeb != 0u && (spins & 3u) == 0u))) {
                     const int cc = min(32, n - cb);
                     const int src = pn + __popc(freeb & ((1u << lane) - 1u));
-                    const int y2 = __shfl_sync(kFull, pd.y, src & 31), pos2 = __shfl_sync(kFull, pd.pos, src & 31);
-                    const float r2 = __shfl_sync(kFull, pd.r, src & 31);
-                    const uint32_t at2 = __shfl_sync(kFull, pd.at, src & 31);
+                    const uint32_t y2 = __shfl_sync(kFull, pd.x, src & 31), pos2 = __shfl_sync(kFull, pd.y, src & 31);
+                    const uint32_t r2 = __shfl_sync(kFull, pd.z, src & 31), at2 = __shfl_sync(kFull, pd.w, src & 31);
                     if (!busy && src < cc && !(at2 & 0x80u)) {  // a terminated agent filed its target in phase A: nothing to do
-                        i = cb + src; y = y2; r = r2; mypos = pos2;
+                        i = cb + src; y = (int)y2; r = __uint_as_float(r2); mypos = (int)pos2;
                         m2 = F.use_masks ? state_mask<ENV>(y, T.A, F.env_seed, full) : full;
                         if (m2 == 0u) atomicOr(T.err, kErrEmpty);  // np.max of an empty selection (QLO:764)
                         sg = __ldcg(seg + y);
@@ -478,30 +515,27 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
                         cbnn = claim_chunk();
                     }
                 }
-                // ---- poll: up to four records of the segment of s' per pass, in position (= agent) order
+                // ---- poll: the (up to eight) records of the two aligned 32-byte groups at the cursor, in position (= agent) order
                 if (busy && !fresh) {
                     bool fin = p >= pe;
                     if (!fin) {
-                        const uint32_t ne = min(pe - p, 4u);
-                        uint4 e[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) e[j] = ld_relaxed_v4(rec + p + min((uint32_t)j, ne - 1u));
+                        const uint32_t pa = p & ~3u;
+                        const U8 ea = ld_relaxed_v8(rec + pa), eb = ld_relaxed_v8(rec + pa + 4);
                         bool stop = false;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (!stop && !fin) {
-                                if ((uint32_t)j >= ne) {
-                                    fin = true;
-                                } else if ((first && (e[j].w >> 2) != (uint32_t)y) || (int)(e[j].x & 0xFFFFFFu) >= i) {
-                                    fin = true;  // stale bounds (nobody stands on s' in this step), or the writers from here on come after i
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t ex = j < 4 ? ea.w[2 * j] : eb.w[2 * (j - 4)], et = j < 4 ? ea.w[2 * j + 1] : eb.w[2 * (j - 4) + 1];
+                            if (!stop && !fin && pa + j >= p) {
+                                if (pa + j >= pe || (int)(ex & 0xFFFFFFu) >= i) {
+                                    fin = true;  // the segment ends here, or the writers from here on come after i
                                 } else {
-                                    uint32_t tb = e[j].y;
-                                    if (tb == kPending && (e[j].w & 1u))  // a self loop: the row being replayed is the row it bootstraps from
-                                        tb = __float_as_uint(td_target_s(__uint_as_float(e[j].z), row_max(), F.gamma));
+                                    uint32_t tb = et;
+                                    if (tb == kPending && (ex & (1u << 29)))  // a self loop: the row being replayed is the row it bootstraps from
+                                        tb = __float_as_uint(td_target_s(__uint_as_float(__ldcg(reinterpret_cast<const uint32_t*>(X.tw + (ex & 0xFFFFFFu)) + 2)),
+                                                                         row_max(), F.gamma));
                                     if (tb != kPending) {
-                                        replay(e[j].x, tb);
+                                        replay(ex, tb);
                                         ++p;
-                                        first = false;
                                     } else {
                                         stop = true;
                                         ++waits;
@@ -529,7 +563,6 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
                     }
                     p = sg.x; pe = sg.y;
                     if (!(p < pe && pe <= (uint32_t)n)) p = pe = 0u;
-                    first = true;
                 }
                 if (cb >= n && !__any_sync(kFull, busy)) break;
                 if ((spins & 255u) == 255u) {
@@ -547,11 +580,12 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
                     PIPE_STAT(8, 1);                                   // warps
                     PIPE_STAT(9, (global_ns() - t_start) >> 4);         // time in phase T, 16 ns units
                     PIPE_STAT(11, wsum);                                // failed polls (lanes)
+                    PIPE_STAT(12, spins_total);                         // passes of the loop
                     atomicMax(X.ctr + 14, (unsigned int)((global_ns() - t_start) >> 4));
                 }
             }
 #endif
-            (void)waits;
+            (void)waits; (void)spins_total;
         }
         grid.sync();
         if (clk && k < 10) F.phase_ns[2 + 3 * k] = global_ns();
@@ -562,18 +596,18 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
         for (int tile = gwarp; tile < ntiles; tile += nwarps) {
             const int p = tile * 32 + lane;
             const bool act = p < n;
-            uint4 e = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
-            if (act) e = __ldcg(rec + p);
-            const uint32_t st = e.w >> 2;
+            uint2 e = make_uint2(0u, 0u);
+            uint32_t st = 0xFFFFFFFFu;  // key (state - state_base) of this position
+            if (act) { e = __ldcg(rec + p); st = (uint32_t)__ldcg(&sorted[p].x); }
             uint32_t prev = __shfl_up_sync(kFull, st, 1);
-            if (lane == 0) prev = p > 0 ? (__ldcg(reinterpret_cast<const uint32_t*>(rec + p - 1) + 3) >> 2) : 0xFFFFFFFFu;
+            if (lane == 0) prev = p > 0 ? (uint32_t)__ldcg(&sorted[p - 1].x) : 0xFFFFFFFFu;
             const bool head = act && (p == 0 || prev != st);
             const uint32_t hb = __ballot_sync(kFull, head);
             const uint32_t below = hb & (0xFFFFFFFFu >> (31 - lane));
             const int hl = below ? 31 - __clz(below) : -1;  // head lane of this lane's segment; -1: the segment began in an earlier tile
             if (act && e.y == kPending) atomicOr(T.err, kErrTimeout);  // cannot happen: phase T published every target
             if (head) {
-                const float* row = T.q + (size_t)st * T.ld;
+                const float* row = T.q + ((size_t)st + (size_t)sbase) * T.ld;
 #pragma unroll
                 for (int c = 0; c < LPR; ++c) {
                     const F8 v8 = ld_row8(row + 8 * c);
@@ -588,7 +622,7 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
             for (int it = 0; it <= maxoff; ++it) {
                 if (off == it) {
                     const int c = wbase + hl;
-                    const uint32_t a = e.x >> 24;
+                    const uint32_t a = (e.x >> 24) & 31u;
                     float* cell = s_row + a * 256 + c;
                     *cell = td_from_target_s(*cell, __uint_as_float(e.y), lr);
                     s_touch[c] |= 1u << a;
@@ -603,12 +637,13 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
                 float v = lane < 8 * LPR ? s_row[lane * 256 + c] : 0.0f;
                 bool touched = false;
                 for (int q = tile * 32 + 32; q < n; q += 32) {
-                    uint4 e2 = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
-                    if (q + lane < n) e2 = __ldcg(rec + q + lane);
-                    const uint32_t diff = __ballot_sync(kFull, (e2.w >> 2) != st31);
+                    uint2 e2 = make_uint2(0u, 0u);
+                    uint32_t k2 = 0xFFFFFFFFu;
+                    if (q + lane < n) { e2 = __ldcg(rec + q + lane); k2 = (uint32_t)__ldcg(&sorted[q + lane].x); }
+                    const uint32_t diff = __ballot_sync(kFull, k2 != st31);
                     const int len = diff ? __ffs(diff) - 1 : 32;
                     for (int j = 0; j < len; ++j) {
-                        const uint32_t xa = __shfl_sync(kFull, e2.x, j) >> 24;
+                        const uint32_t xa = (__shfl_sync(kFull, e2.x, j) >> 24) & 31u;
                         const float tg = __uint_as_float(__shfl_sync(kFull, e2.y, j));
                         if ((uint32_t)lane == xa) { v = td_from_target_s(v, tg, lr); touched = true; }
                     }
@@ -620,7 +655,7 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
             }
             __syncwarp();
             if (head) {
-                float* row = T.q + (size_t)st * T.ld;
+                float* row = T.q + ((size_t)st + (size_t)sbase) * T.ld;
                 for (uint32_t bm = s_touch[threadIdx.x]; bm; bm &= bm - 1u) {
                     const int a = __ffs(bm) - 1;
                     row[a] = s_row[a * 256 + threadIdx.x];
@@ -628,10 +663,18 @@ __global__ void __launch_bounds__(256, QE_PIPE_MIN_BLOCKS) fused_pipe_kernel(Tab
             }
             __syncwarp();
         }
-        if (tid == 0) X.ctr[par] = 0u;  // this parity's claim counter is idle until the step after the next one
-        grid.sync();
+        if (clk && k < 10) F.phase_ns[32 + k] = global_ns();  // (this thread's end of phase C)
+
+        // ---------------- phase S: the next step's order.  Its first stage only reads the next states, so no barrier is
+        // needed after phase C; its last barrier orders pos[] before the next phase A, the bounds are needed by phase T.
+        __syncthreads();  // the histograms share their shared memory with phase C's rows
+        {
+            const int src = pipe_sort<WARPS>(grid, s_whist, s_base, s_wsum, nxt, n, old_n, X);
+            pipe_bounds<WARPS>(X.kv[src], n, X);
+        }
         if (clk && k < 10) F.phase_ns[3 + 3 * k] = global_ns();
     }
+    grid.sync();
     if (F.steps & 1) {
         for (int i = tid; i < n; i += nthreads) F.st_a[i] = F.st_b[i];
     }

@@ -34,6 +34,7 @@ def launch(t0, stats=True):
     run.t0 = run.env_t0 = t0
     run.use_masks = 1
     run.evaluate = int(os.environ.get('QE_EVAL', '0'))
+    run.learn_mode = int(os.environ.get('QE_ACC', '0'))
     run.empty_all = int(A > 10)
     if stats:
         run.episode_sum, run.episode_count = es.data_ptr(), ec.data_ptr()
@@ -56,21 +57,23 @@ for r in range(reps):
     best = min(best, ms)
     print(f"rep {r}: {ms:.3f} ms for {K} steps -> {ms / K * 1e3:.1f} us/step, {N * K / ms / 1e6:.3f} G agent-steps/s")
 capi.check(lib.qe_sync(h, None))
-buf = (C.c_uint64 * 33)()
-m = lib.qe_fused_phase_ns(h, buf, 33)
+buf = (C.c_uint64 * 48)()
+m = lib.qe_fused_phase_ns(h, buf, 48)
 ts = [buf[i] for i in range(m)]
 if m >= 4:
     for ph, name in enumerate(("A ", "B1", "B2")):
         print(f"phase {name} us:", " ".join(f"{(ts[1 + ph + 3 * k] - ts[ph + 3 * k]) / 1e3:.1f}" for k in range((m - 1) // 3)))
+if lib.qe_fused_form(h) == 3 and m >= 4:
+    print("  pipelined form: A = select + env step, B1 = target pipeline, B2 = commit + sort of the next states; commit us:",
+          " ".join(f"{(buf[32 + k] - ts[2 + 3 * k]) / 1e3:.1f}" for k in range((m - 1) // 3)), "| sort us:", " ".join(f"{(ts[3 + 3 * k] - buf[32 + k]) / 1e3:.1f}" for k in range((m - 1) // 3)))
 cnt = (C.c_uint64 * 56)()
 if lib.qe_fused_form(h) == 3:
     if lib.qe_debug_counters(h, cnt, 2) == 0 and cnt[0]:
-        for name, o in (("first sort of the launch (alone)", 8), ("sorts under phase T", 24)):
-            print(f"{name}: latest warp at stage end, us since it entered the sort (hist, barrier, column scan, barrier, bases, scatter, barrier): pass 0",
-                  [round(cnt[o + j] / 1e3, 1) for j in range(7)], "pass 1", [round(cnt[o + 8 + j] / 1e3, 1) for j in range(7)])
+        print("sort laps of block 0, us per sort (hist, barrier, column scan, barrier, bases, scatter, barrier): pass 0", [round(cnt[8 + j] / 1e3 / K, 1) for j in range(7)],
+              "pass 1", [round(cnt[16 + j] / 1e3 / K, 1) for j in range(7)], "segment bounds", round(cnt[24] / 1e3 / K, 1))
         warps = cnt[0]
         print(f"pipeline stats (last launch): warp-steps {warps}, mean time a warp spends in phase T {cnt[1] * 16 / warps / 1e3:.2f} us (slowest {cnt[6] * 16 / 1e3:.1f}), sort {cnt[2] / max(K - 1, 1) / 1e3:.1f} us per step, "
-              f"failed polls per agent {cnt[3] / (N * K):.3f}")
+              f"failed polls per agent {cnt[3] / (N * K):.3f}, loop passes per warp-step {cnt[4] / warps:.1f}")
 elif lib.qe_debug_counters(h, cnt, 1) == 0 and cnt[5]:
     nw = cnt[5]
     print(f'phase Q per warp-step: sweeps before resident {cnt[0]/nw:.2f}, us until resident mean {cnt[1]/nw/1e3:.1f} max {cnt[2]/1e3:.1f}, resident us mean {cnt[3]/nw/1e3:.1f} max {cnt[4]/1e3:.1f}, jobs at switch {cnt[6]/nw:.1f}, warp-steps {nw}')
