@@ -9,13 +9,14 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc", "qe_engine.cu")
-DEPS = [SRC, os.path.join(PKG, "csrc", "qe_pipe.cuh"), os.path.join(PKG, "csrc", "qe_kernels.cuh"), os.path.join(PKG, "csrc", "qe_common.cuh"), os.path.join(PKG, "csrc", "qe_sorted.cuh"), os.path.join(PKG, "csrc", "qe_radix.cuh"),
+SRC2 = os.path.join(PKG, "csrc", "qe_shard.cu")  # the peer-memory sharded table: its own translation unit (compiled in parallel)
+DEPS = [SRC, SRC2, os.path.join(PKG, "csrc", "qe_shard.cuh"), os.path.join(PKG, "csrc", "qe_pipe.cuh"), os.path.join(PKG, "csrc", "qe_kernels.cuh"), os.path.join(PKG, "csrc", "qe_common.cuh"), os.path.join(PKG, "csrc", "qe_sorted.cuh"), os.path.join(PKG, "csrc", "qe_radix.cuh"),
         os.path.join(os.path.dirname(PKG), "include", "qe_engine.h")]
 OUT = os.path.join(PKG, "_lib", "libqe_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
-    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--threads", "2",
 ]
 
 
@@ -34,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc(), *NVCC_FLAGS, "-o", OUT, SRC]
+    cmd = [nvcc(), *NVCC_FLAGS, "-o", OUT, SRC, SRC2]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(PKG, "_lib", "build.log")
     with open(log, "w") as f:

@@ -41,6 +41,19 @@ SIGNATURES = {
     "qe_create": (C.c_int, [i64, i32, f32, i32, C.POINTER(vp)]),
     "qe_destroy": (C.c_int, [vp]),
     "qe_last_error": (C.c_char_p, []),
+    "qe_set_last_error": (C.c_int, [C.c_int, C.c_char_p]),
+    "qe_shard_create": (C.c_int, [i64, i32, f32, i32, i32, i32, i32, u32, C.POINTER(vp)]),
+    "qe_shard_destroy": (C.c_int, [vp]),
+    "qe_shard_ipc_handle": (C.c_int, [vp, vp]),
+    "qe_shard_connect_ipc": (C.c_int, [vp, i32, vp]),
+    "qe_shard_connect_local": (C.c_int, [vp, i32, vp]),
+    "qe_shard_fill_random": (C.c_int, [vp, u32, vp]),
+    "qe_shard_reset": (C.c_int, [vp, u32, u32, vp]),
+    "qe_shard_steps": (C.c_int, [vp, i32, i32, vp, vp, u32, u32, i32, i32, u64, vp]),
+    "qe_shard_sync": (C.c_int, [vp, vp]),
+    "qe_shard_download": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+    "qe_shard_rows_host": (C.c_int, [vp, vp, vp, i32]),
+    "qe_shard_info": (i32, [vp, i32]),
     "qe_set_discount": (C.c_int, [vp, f32]),
     "qe_table_ptr": (vp, [vp]),
     "qe_table_stride": (i32, [vp]),

@@ -24,6 +24,10 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+extern "C" int qe_set_last_error(int code, const char* msg) {  // for the library's other translation units
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
 #define CK(call)                                                                                          \
     do {                                                                                                  \
         cudaError_t _e = (call);                                                                          \

@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(256) select_kernel(Table T, const int32_t* __r
 }
 
 // general action counts (A > 32 or byte masks): one thread per agent, three passes over the row
-__global__ void select_generic_kernel(Table T, const int32_t* __restrict__ states, const uint8_t* __restrict__ mask_bytes,
+static __global__ void select_generic_kernel(Table T, const int32_t* __restrict__ states, const uint8_t* __restrict__ mask_bytes,
                                       Uniforms U, uint64_t thresh, int deterministic, int empty_all,
                                       int32_t* __restrict__ actions, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(256) learn_exact_kernel(Table T, const int32_t
 }
 
 // general fallback (A > 32 / byte masks): the reference loop itself, one warp walks the agents in order
-__global__ void learn_sequential_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions,
+static __global__ void learn_sequential_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions,
                                         const float* __restrict__ rewards, const int32_t* __restrict__ next_states,
                                         const uint8_t* __restrict__ terminated, const uint8_t* __restrict__ next_mask_bytes,
                                         const uint32_t* __restrict__ next_mask_bits, float lr, float gamma, int n) {
@@ -939,7 +939,7 @@ __global__ void learn_sequential_kernel(Table T, const int32_t* __restrict__ sta
 }
 
 // accumulate mode (learn_vec, QLO:853-891): deltas from the snapshot, then atomic scatter-add
-__global__ void learn_delta_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions,
+static __global__ void learn_delta_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions,
                                    const float* __restrict__ rewards, const int32_t* __restrict__ next_states,
                                    const uint8_t* __restrict__ terminated, const uint8_t* __restrict__ next_mask_bytes,
                                    const uint32_t* __restrict__ next_mask_bits, float lr, float gamma, float* __restrict__ delta,
@@ -957,19 +957,19 @@ __global__ void learn_delta_kernel(Table T, const int32_t* __restrict__ states, 
     const float target = rewards[i] + gamma * m * (terminated[i] ? 0.0f : 1.0f);
     delta[i] = lr * (target - T.q[(size_t)states[i] * T.ld + actions[i]]);
 }
-__global__ void learn_scatter_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions,
+static __global__ void learn_scatter_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions,
                                      const float* __restrict__ delta, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicAdd(T.q + (size_t)states[i] * T.ld + actions[i], delta[i]);
 }
 
-__global__ void gather_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions,
+static __global__ void gather_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions,
                               float* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = T.q[(size_t)states[i] * T.ld + actions[i]];
 }
 
-__global__ void gather_rows_kernel(Table T, const int32_t* __restrict__ states, float* __restrict__ out, int n) {
+static __global__ void gather_rows_kernel(Table T, const int32_t* __restrict__ states, float* __restrict__ out, int n) {
     const size_t total = (size_t)n * T.A;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
@@ -978,7 +978,7 @@ __global__ void gather_rows_kernel(Table T, const int32_t* __restrict__ states, 
     }
 }
 
-__global__ void table_fill_kernel(Table T, int64_t S, float value, uint32_t seed, int random, uint64_t state_base) {
+static __global__ void table_fill_kernel(Table T, int64_t S, float value, uint32_t seed, int random, uint64_t state_base) {
     const size_t total = (size_t)S * T.ld;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
@@ -992,7 +992,7 @@ __global__ void table_fill_kernel(Table T, int64_t S, float value, uint32_t seed
 
 // ------------------------------------------------------------------ sharded / replicated table helpers
 // commit of a held TD update: the last writer of every cell stores its published value
-__global__ void learn_commit_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions, int n) {
+static __global__ void learn_commit_kernel(Table T, const int32_t* __restrict__ states, const int32_t* __restrict__ actions, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && !T.later_buf[i]) T.q[(size_t)states[i] * T.ld + actions[i]] = __uint_as_float((uint32_t)ld_relaxed_u64(T.slot + i));
 }
@@ -1000,7 +1000,7 @@ __global__ void learn_commit_kernel(Table T, const int32_t* __restrict__ states,
 // (row, a') just before an agent that sorts before local agent `pos` (all local agents < pos are earlier, all others
 // later).  Values of earlier writers come from their published slots (the held update of this epoch), everything
 // else from the untouched table.  use_versions = 0: plain snapshot max.
-__global__ void serve_bootstrap_kernel(Table T, const int32_t* __restrict__ rows, const int32_t* __restrict__ pos,
+static __global__ void serve_bootstrap_kernel(Table T, const int32_t* __restrict__ rows, const int32_t* __restrict__ pos,
                                        const uint32_t* __restrict__ masks, float* __restrict__ out, int n, uint32_t epoch,
                                        int use_versions) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1035,7 +1035,7 @@ __global__ void serve_bootstrap_kernel(Table T, const int32_t* __restrict__ rows
     out[r] = m;
 }
 // replicated table: delta[s][a] = Q[s][a] - base[s][a]   (dense [S][A] buffers)
-__global__ void table_delta_kernel(Table T, int64_t S, const float* __restrict__ base, float* __restrict__ delta) {
+static __global__ void table_delta_kernel(Table T, int64_t S, const float* __restrict__ base, float* __restrict__ delta) {
     const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
         const size_t s = x / T.A;
@@ -1043,7 +1043,7 @@ __global__ void table_delta_kernel(Table T, int64_t S, const float* __restrict__
     }
 }
 // ... and Q = base = base + sum of the ranks' deltas
-__global__ void table_merge_kernel(Table T, int64_t S, float* __restrict__ base, const float* __restrict__ delta_sum) {
+static __global__ void table_merge_kernel(Table T, int64_t S, float* __restrict__ base, const float* __restrict__ delta_sum) {
     const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
         const size_t s = x / T.A;
@@ -1052,14 +1052,14 @@ __global__ void table_merge_kernel(Table T, int64_t S, float* __restrict__ base,
         T.q[s * T.ld + (x - s * T.A)] = v;
     }
 }
-__global__ void table_export_kernel(Table T, int64_t S, float* __restrict__ dense) {
+static __global__ void table_export_kernel(Table T, int64_t S, float* __restrict__ dense) {
     const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
         const size_t s = x / T.A;
         dense[x] = T.q[s * T.ld + (x - s * T.A)];
     }
 }
-__global__ void table_import_kernel(Table T, int64_t S, const float* __restrict__ dense) {
+static __global__ void table_import_kernel(Table T, int64_t S, const float* __restrict__ dense) {
     const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
         const size_t s = x / T.A;
@@ -1068,7 +1068,7 @@ __global__ void table_import_kernel(Table T, int64_t S, const float* __restrict_
 }
 
 // ------------------------------------------------------------------ unfused environments (one thread per agent)
-__global__ void ttt_reset_kernel(uint32_t* __restrict__ boards, int32_t* __restrict__ states, uint32_t* __restrict__ masks,
+static __global__ void ttt_reset_kernel(uint32_t* __restrict__ boards, int32_t* __restrict__ states, uint32_t* __restrict__ masks,
                                  Uniforms U, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1077,7 +1077,7 @@ __global__ void ttt_reset_kernel(uint32_t* __restrict__ boards, int32_t* __restr
     states[i] = ttt_state(b & 0x3FFFFu);
     masks[i] = ttt_empties(b);
 }
-__global__ void ttt_step_kernel(uint32_t* __restrict__ boards, const int32_t* __restrict__ actions, Uniforms U,
+static __global__ void ttt_step_kernel(uint32_t* __restrict__ boards, const int32_t* __restrict__ actions, Uniforms U,
                                 int32_t* __restrict__ next_states, uint32_t* __restrict__ next_masks, float* __restrict__ rewards,
                                 uint8_t* __restrict__ terminated, int* err, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1092,7 +1092,7 @@ __global__ void ttt_step_kernel(uint32_t* __restrict__ boards, const int32_t* __
     rewards[i] = r;
     terminated[i] = term;
 }
-__global__ void mdp_reset_kernel(int32_t* __restrict__ states, uint32_t* __restrict__ masks, uint32_t S, int A, uint32_t env_seed,
+static __global__ void mdp_reset_kernel(int32_t* __restrict__ states, uint32_t* __restrict__ masks, uint32_t S, int A, uint32_t env_seed,
                                  Uniforms U, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1100,7 +1100,7 @@ __global__ void mdp_reset_kernel(int32_t* __restrict__ states, uint32_t* __restr
     states[i] = s;
     if (masks) masks[i] = mdp_mask((uint32_t)s, A, env_seed);
 }
-__global__ void mdp_step_kernel(int32_t* __restrict__ states, const int32_t* __restrict__ actions, uint32_t S, int A,
+static __global__ void mdp_step_kernel(int32_t* __restrict__ states, const int32_t* __restrict__ actions, uint32_t S, int A,
                                 uint32_t env_seed, uint64_t term_thresh, Uniforms U, uint32_t* __restrict__ next_masks,
                                 float* __restrict__ rewards, uint8_t* __restrict__ terminated, int* err, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1117,7 +1117,7 @@ __global__ void mdp_step_kernel(int32_t* __restrict__ states, const int32_t* __r
     terminated[i] = term;
 }
 
-__global__ void mdp_masks_kernel(const int32_t* __restrict__ states, uint32_t* __restrict__ masks, int A, uint32_t env_seed, int n) {
+static __global__ void mdp_masks_kernel(const int32_t* __restrict__ states, uint32_t* __restrict__ masks, int A, uint32_t env_seed, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) masks[i] = mdp_mask((uint32_t)states[i], A, env_seed);
 }

@@ -14,7 +14,7 @@ struct RadixSpec {
 };
 
 // out[i] = sum_d vectors[i][d] * radix[d]          (encode_multi_discretes, utils.py:51-69)
-__global__ void __launch_bounds__(256) radix_encode_kernel(const int32_t* __restrict__ vectors, RadixSpec R, long long* __restrict__ out, long long n) {
+static __global__ void __launch_bounds__(256) radix_encode_kernel(const int32_t* __restrict__ vectors, RadixSpec R, long long* __restrict__ out, long long n) {
     extern __shared__ int32_t s_tile[];  // [256][dims], padded to an odd stride
     const int D = R.dims, ld = D | 1;
     for (long long base = (long long)blockIdx.x * 256; base < n; base += (long long)gridDim.x * 256) {
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) radix_encode_kernel(const int32_t* __rest
 }
 
 // out[i][d] = (indices[i] // radix[d]) % nvec[d]    (decode_to_multi_discretes, utils.py:95-115; floor semantics)
-__global__ void __launch_bounds__(256) radix_decode_kernel(const long long* __restrict__ indices, RadixSpec R, int32_t* __restrict__ out, long long n) {
+static __global__ void __launch_bounds__(256) radix_decode_kernel(const long long* __restrict__ indices, RadixSpec R, int32_t* __restrict__ out, long long n) {
     extern __shared__ int32_t s_tile[];
     const int D = R.dims, ld = D | 1;
     for (long long base = (long long)blockIdx.x * 256; base < n; base += (long long)gridDim.x * 256) {

@@ -203,7 +203,7 @@ __device__ __forceinline__ void radix_pass(cg::grid_group& grid, int (*whist)[kR
 }
 
 // development aid: cost of one grid barrier at the fused loop's launch shape
-__global__ void __launch_bounds__(256, 4) gridsync_probe_kernel(int iters, uint64_t* out) {
+static __global__ void __launch_bounds__(256, 4) gridsync_probe_kernel(int iters, uint64_t* out) {
     cg::grid_group grid = cg::this_grid();
     const uint64_t t0 = global_ns();
     for (int i = 0; i < iters; ++i) grid.sync();

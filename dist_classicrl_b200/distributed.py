@@ -289,11 +289,21 @@ def merge_deltas(transport: Transport, local, base):
 
 # ----------------------------------------------------------------------------------------------------- sharded table
 class ShardedQLearning:
-    """State-range-sharded Q-table with the hash MDP's agents living on the shard of their state (config 4).
+    """State-range-sharded Q-table over peer memory (BASELINE config 4; ``csrc/qe_shard.cuh``).
 
-    Parameters mirror ``OptimalQLearningBase`` (QLO:84-90) plus the environment of ``HashMDPVecEnv``.  Results
-    (table, agent states, episode returns) are identical to the single-GPU engine run on the same seeds.
+    Rank ``g`` owns the states ``[g * rows, (g + 1) * rows)``, ``rows = ceil(S / G)``, and for good the agents
+    ``[g * ceil(N / G), ...)``.  One persistent kernel per GPU runs whole vector steps: rows, writer records and
+    targets travel as peer loads / stores over NVLink, the per-step order is a distributed stable sort, phases are
+    separated by flag barriers in peer memory -- no host synchronisation and no collective on the data path
+    (``torch.distributed`` only carries the 64-byte CUDA IPC handles at construction and the gathers of the
+    ``gather_*`` helpers).  With a :class:`LoopbackTransport` the ``G`` ranks share one GPU and run side by side in one
+    cooperative launch (the one-GPU parity tests).
+
+    Parameters mirror ``OptimalQLearningBase`` (QLO:84-90) plus the environment of ``HashMDPVecEnv``.  Results (table,
+    agent states, episode returns) are identical to the single-GPU engine run on the same seeds.
     """
+
+    launch_steps = 8  # vector steps per kernel launch
 
     def __init__(self, state_size: int, action_size: int, discount_factor: float, num_agents: int, transport: Transport,
                  env_seed: int = 0, p_term: float = 0.05, seed: int = 0, device: int | None = None) -> None:
@@ -313,23 +323,56 @@ class ShardedQLearning:
         self.lo, self.hi = shard_range(state_size, self.world, self.rank)
         self._lib = capi.lib()
         self._h = C.c_void_p()
-        capi.check(self._lib.qe_create(max(self.hi - self.lo, 1), self.action_size, self.discount_factor, self.device_index, C.byref(self._h)))
-        capi.check(self._lib.qe_set_state_base(self._h, self.lo))
-        self.gamma32 = torch.tensor(np.float32(discount_factor), dtype=torch.float32, device=self.dev)
-        self.t = 0  # vector-step counter of both uniform streams
-        self.gid = self.state = self.ep_ret = None
+        capi.check(self._lib.qe_shard_create(self.state_size, self.action_size, self.discount_factor, self.device_index, self.rank,
+                                             self.world, self.num_agents, self.env_seed, C.byref(self._h)))
+        self.n_home = int(self._lib.qe_shard_info(self._h, 1))
+        self.n_here = int(self._lib.qe_shard_info(self._h, 2))
+        self._peers: list | None = None  # loopback: every rank's handle (rank 0 launches for all of them)
+        self._connect()
         self.episode_count, self.episode_sum = 0, 0.0
-        self.rounds_last = 0
-        self.rounds_total = 0
-        self.profile: dict | None = None  # set to {} to collect per-section wall times (synchronising; diagnostics only)
+        self.profile: dict | None = None
+
+    def _connect(self) -> None:
+        lib = self._lib
+        if isinstance(self.tp, LoopbackTransport):
+            handles = self.tp._exchange(int(self._h.value))
+            for g, hg in enumerate(handles):
+                if g != self.rank:
+                    capi.check(lib.qe_shard_connect_local(self._h, g, C.c_void_p(hg)))
+            self._peers = handles
+            self.tp.barrier()
+            return
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+
+        buf = (C.c_ubyte * 64)()
+        capi.check(lib.qe_shard_ipc_handle(self._h, buf))
+        mine = bytes(buf)
+        every = [None] * self.world
+        dist.all_gather_object(every, mine, group=getattr(self.tp, "group", None))
+        for g, hb in enumerate(every):
+            if g != self.rank:
+                raw = (C.c_ubyte * 64).from_buffer_copy(hb)
+                capi.check(lib.qe_shard_connect_ipc(self._h, g, raw))
+        self.tp.barrier()
 
     def __del__(self) -> None:
         h, self._h = getattr(self, "_h", None), None
         if h:
             try:
-                self._lib.qe_destroy(h)
+                self._lib.qe_shard_destroy(h)
             except Exception:  # noqa: BLE001
                 pass
+
+    def close(self) -> None:
+        """Collective: every rank stops using the peers' memory before anybody frees it."""
+        _torch().cuda.synchronize()
+        self.tp.barrier()
+        h, self._h = self._h, None
+        if h:
+            self._lib.qe_shard_destroy(h)
+        self.tp.barrier()
 
     # -- helpers
     def _stream(self):
@@ -337,172 +380,100 @@ class ShardedQLearning:
 
     def fill_random(self, seed: int = 1) -> None:
         """Same values as the single-GPU ``fill_random``: every shard fills its slice of the whole table."""
-        capi.check(self._lib.qe_table_fill_random(self._h, seed, self._stream()))
+        capi.check(self._lib.qe_shard_fill_random(self._h, seed, self._stream()))
 
-    def local_table(self) -> np.ndarray:
-        out = np.empty((max(self.hi - self.lo, 1), self.action_size), dtype=np.float32)
-        capi.check(self._lib.qe_table_download_host(self._h, out.ctypes.data_as(C.c_void_p)))
-        return out[: self.hi - self.lo]
-
-    def _masks(self, states):
-        torch = _torch()
-        out = torch.empty(states.shape[0], dtype=torch.int32, device=self.dev)
-        capi.check(self._lib.qe_mdp_masks(states.data_ptr(), out.data_ptr(), self.action_size, self.env_seed, states.shape[0], self._stream()))
-        return out
-
-    def _migrate(self, gid, state, ep_ret):
-        torch = _torch()
-        rows = torch.stack([gid, state, ep_ret.view(torch.int32)], dim=1)
-        recv, _, _ = route(self.tp, rows, owner_of(state, self.state_size, self.world).to(torch.int64))
-        order = torch.sort(recv[:, 0], stable=True).indices  # global-id order == the sequential order of the update
-        recv = recv[order]
-        self.gid = recv[:, 0].contiguous()
-        self.state = recv[:, 1].contiguous()
-        self.ep_ret = recv[:, 2].contiguous().view(torch.float32)
-
-    # -- environment
     def reset(self) -> None:
-        """Initial states of the agents this rank draws (a contiguous global-id range), then migration to the owners."""
-        torch = _torch()
-        n, g = self.num_agents, self.world
-        per = -(-n // g)
-        a0, a1 = min(self.rank * per, n), min((self.rank + 1) * per, n)
-        cnt = a1 - a0
-        state = torch.empty(max(cnt, 1), dtype=torch.int32, device=self.dev)[:cnt]
-        if cnt:
-            capi.check(self._lib.qe_mdp_reset(state.data_ptr(), None, self.state_size, self.action_size, self.env_seed, None, 4,
-                                              self.seed, T_INIT, a0, cnt, self._stream()))
-        gid = torch.arange(a0, a1, dtype=torch.int32, device=self.dev)
-        self._migrate(gid, state, torch.zeros(cnt, dtype=torch.float32, device=self.dev))
-        self.t = 0
+        """Initial states of this rank's agents (the hash MDP's reset draw by global id)."""
+        capi.check(self._lib.qe_shard_reset(self._h, self.seed, T_INIT, self._stream()))
+        _torch().cuda.synchronize()
+        self.tp.barrier()
 
-    def _mark(self, name: str) -> None:
-        if self.profile is not None:
-            import time
+    def _launch(self, thresholds: np.ndarray, lrs: np.ndarray) -> None:
+        lib, k = self._lib, int(thresholds.shape[0])
+        args = (k, thresholds.ctypes.data_as(C.c_void_p), lrs.ctypes.data_as(C.c_void_p), self.seed, self.seed,
+                int(self.action_size > 10), 1, self.term_threshold, self._stream())
+        if self._peers is not None:  # all ranks on this GPU: one cooperative launch, issued by rank 0
+            self.tp.barrier()
+            if self.rank == 0:
+                arr = (C.c_void_p * self.world)(*[C.c_void_p(hg) for hg in self._peers])
+                capi.check(lib.qe_shard_steps(arr, self.world, *args))
+                _torch().cuda.synchronize()
+            self.tp.barrier()
+            capi.check(lib.qe_shard_sync(self._h, self._stream()))
+        else:
+            arr = (C.c_void_p * 1)(self._h)
+            capi.check(lib.qe_shard_steps(arr, 1, *args))
 
-            _torch().cuda.synchronize()
-            now = time.perf_counter()
-            self.profile[name] = self.profile.get(name, 0.0) + (now - self._t_mark)
-            self._t_mark = now
-
-    # -- one vector step
     def step(self, eps: float, lr: float) -> None:
-        torch, lib, h = _torch(), self._lib, self._h
-        st = self._stream()
-        if self.profile is not None:
-            import time
-
-            torch.cuda.synchronize()
-            self._t_mark = time.perf_counter()
-        n = int(self.gid.shape[0])
-        thresh = explore_threshold(eps)
-        gid, s_old = self.gid, self.state
-        s2 = s_old.clone()
-        actions = torch.empty(max(n, 1), dtype=torch.int32, device=self.dev)[:n]
-        rewards = torch.empty(max(n, 1), dtype=torch.float32, device=self.dev)[:n]
-        term = torch.empty(max(n, 1), dtype=torch.uint8, device=self.dev)[:n]
-        mask2 = torch.empty(max(n, 1), dtype=torch.int32, device=self.dev)[:n]
-        if n:
-            capi.check(lib.qe_set_agent_ids(h, gid.data_ptr()))
-            masks = self._masks(s_old)
-            capi.check(lib.qe_select(h, s_old.data_ptr(), masks.data_ptr(), None, None, 4, self.seed, self.t, 0, thresh, 0,
-                                     int(self.action_size > 10), actions.data_ptr(), n, st))
-            capi.check(lib.qe_mdp_step(h, s2.data_ptr(), actions.data_ptr(), self.state_size, self.action_size, self.env_seed,
-                                       self.term_threshold, None, 4, self.seed, self.t, 0, mask2.data_ptr(), rewards.data_ptr(),
-                                       term.data_ptr(), n, st))
-            capi.check(lib.qe_set_agent_ids(h, None))
-        self._mark("select+env")
-        # episode bookkeeping (BRT:212-221)
-        acc = self.ep_ret + rewards
-        done = term != 0
-        if n:
-            self.episode_count += int(done.sum().item())
-            self.episode_sum += float(acc[done].double().sum().item())
-        self.ep_ret = torch.where(done, torch.zeros_like(acc), acc)
-
-        self._mark("bookkeeping")
-        # ---- TD update, exact in global agent order
-        own2 = owner_of(s2, self.state_size, self.world).to(torch.int64)
-        remote = (~done) & (own2 != self.rank)
-        ridx = torch.nonzero(remote).reshape(-1)
-        req_rows = torch.stack([gid[ridx], s2[ridx]], dim=1) if n else torch.empty((0, 2), dtype=torch.int32, device=self.dev)
-        order, out_counts = bucket_by_owner(own2[ridx], self.world)
-        recv = self.tp.all_to_all_v(list(torch.split(req_rows[order], out_counts, dim=0)))
-        in_counts = [int(x.shape[0]) for x in recv]
-        got = torch.cat(recv, dim=0)
-        nreq = int(got.shape[0])
-        req_s2 = got[:, 1].contiguous()
-        req_pos = torch.searchsorted(gid, got[:, 0].contiguous()).to(torch.int32) if nreq else got[:, 0].contiguous()
-        req_mask = self._masks(req_s2) if nreq else req_s2
-        answers = torch.empty((max(nreq, 1), 1), dtype=torch.float32, device=self.dev)[:nreq]
-
-        def serve(use_versions: int):
-            if nreq:
-                capi.check(lib.qe_serve_bootstrap(h, req_s2.data_ptr(), req_pos.data_ptr(), req_mask.data_ptr(), answers.data_ptr(),
-                                                  nreq, use_versions, st))
-            return route_back(self.tp, answers.view(torch.int32), in_counts, order, out_counts).view(torch.float32).reshape(-1)
-
-        self._mark("route requests")
-        m_ext = serve(0)  # snapshot values to start from
-        self._mark("serve0")
-        term_eff = torch.where(remote, torch.ones_like(term), term)
-        s2_safe = torch.where(remote, s_old, s2)  # remote rows are never touched locally
-        lr32 = float(np.float32(lr))
-        capi.check(lib.qe_set_hold(h, 1))
-        rounds = 0
-        while True:
-            r_eff = rewards.clone()
-            if ridx.numel():
-                r_eff[ridx] = rewards[ridx] + self.gamma32 * m_ext  # target of a remote bootstrap: r + gamma*m, one rounding each
-            if n:
-                capi.check(lib.qe_learn(h, s_old.data_ptr(), actions.data_ptr(), r_eff.data_ptr(), s2_safe.data_ptr(), term_eff.data_ptr(),
-                                        mask2.data_ptr(), None, lr32, n, capi.QE_LEARN_SEQUENTIAL, st))
-            rounds += 1
-            self._mark("learn (hold)")
-            m_new = serve(1)
-            self._mark("serve")
-            changed = (m_new.view(torch.int32) != m_ext.view(torch.int32)).any().to(torch.int32).reshape(1)
-            m_ext = m_new
-            stop = self.tp.all_reduce_max_flag(changed) == 0
-            self._mark("converged?")
-            if stop:
-                break
-            if rounds > 4096:
-                raise capi.EngineError("sharded TD update did not reach its fixed point")
-        if n:
-            capi.check(lib.qe_learn_commit(h, s_old.data_ptr(), actions.data_ptr(), n, st))
-        capi.check(lib.qe_set_hold(h, 0))
-        capi.check(lib.qe_sync(h, st))
-        self.rounds_last = rounds
-        self.rounds_total += rounds
-        self.t = (self.t + 1) & 0xFFFFFFFF
-        self._mark("commit")
-        # ---- migration to owner(s')
-        self._migrate(gid, s2, self.ep_ret)
-        self._mark("migrate")
+        self._launch(np.asarray([explore_threshold(eps)], dtype=np.uint64), np.asarray([lr], dtype=np.float32))
 
     def run_steps(self, steps: int, exploration_rate_schedule, lr_schedule) -> None:
-        """``steps`` vector steps with the reference's schedule protocol (values read, then ``update(N)``, BRT:245-263)."""
-        for _ in range(steps):
-            eps, lr = exploration_rate_schedule.get_value(), lr_schedule.get_value()
-            self.step(eps, lr)
-            lr_schedule.update(self.num_agents)
-            exploration_rate_schedule.update(self.num_agents)
+        """``steps`` vector steps with the reference's schedule protocol (values read, then ``update(N)``, BRT:245-263);
+        ``launch_steps`` of them per kernel launch."""
+        done = 0
+        while done < steps:
+            k = min(self.launch_steps, steps - done)
+            th = np.empty(k, dtype=np.uint64)
+            lrs = np.empty(k, dtype=np.float32)
+            for j in range(k):
+                th[j] = explore_threshold(exploration_rate_schedule.get_value())
+                lrs[j] = np.float32(lr_schedule.get_value())
+                lr_schedule.update(self.num_agents)
+                exploration_rate_schedule.update(self.num_agents)
+            self._launch(th, lrs)
+            done += k
+
+    def sync(self) -> None:
+        """Wait for this rank's kernels and raise deferred device errors."""
+        capi.check(self._lib.qe_shard_sync(self._h, self._stream()))
+
+    def _download(self):
+        table = np.empty((max(self.hi - self.lo, 1), self.action_size), dtype=np.float32)
+        states = np.empty(max(self.n_here, 1), dtype=np.int32)
+        rets = np.empty(max(self.n_here, 1), dtype=np.float32)
+        es, ec = C.c_double(0.0), C.c_uint64(0)
+        capi.check(self._lib.qe_shard_sync(self._h, self._stream()))
+        capi.check(self._lib.qe_shard_download(self._h, table.ctypes.data_as(C.c_void_p), states.ctypes.data_as(C.c_void_p),
+                                               rets.ctypes.data_as(C.c_void_p), C.byref(es), C.byref(ec)))
+        self.episode_sum, self.episode_count = float(es.value), int(ec.value)
+        return table[: self.hi - self.lo], states[: self.n_here], rets[: self.n_here]
+
+    def local_table(self) -> np.ndarray:
+        return self._download()[0]
+
+    def rows(self, states) -> np.ndarray:
+        """Rows of THIS shard by global state id (parity checks at table sizes that do not fit the host)."""
+        st = np.ascontiguousarray(states, dtype=np.int64)
+        out = np.empty((st.shape[0], self.action_size), dtype=np.float32)
+        capi.check(self._lib.qe_shard_sync(self._h, self._stream()))
+        capi.check(self._lib.qe_shard_rows_host(self._h, st.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), st.shape[0]))
+        return out
 
     # -- whole-job views (collective)
     def gather_agents(self):
         """``(states, episode_returns)`` of all agents in global-id order, on every rank (collective)."""
         torch = _torch()
-        rows = torch.stack([self.gid, self.state, self.ep_ret.view(torch.int32)], dim=1)
-        allr = self.tp.all_gather_rows(rows)
-        allr = allr[torch.sort(allr[:, 0]).indices]
-        return allr[:, 1].cpu().numpy(), allr[:, 2].contiguous().view(torch.float32).cpu().numpy()
+        _, states, rets = self._download()
+        rows = torch.stack([torch.from_numpy(states.copy()), torch.from_numpy(rets.copy()).view(torch.int32)], dim=1).to(self.dev)
+        allr = self.tp.all_gather_rows(rows)  # rank order == global-id order (contiguous id ranges)
+        return allr[:, 0].cpu().numpy(), allr[:, 1].contiguous().view(torch.float32).cpu().numpy()
 
     def gather_table(self) -> np.ndarray:
         """The whole table ``[S, A]`` on every rank (collective; tests and checkpoints)."""
         torch = _torch()
-        part = torch.from_numpy(self.local_table()).to(self.dev)
+        part = torch.from_numpy(self._download()[0].copy()).to(self.dev)
         return self.tp.all_gather_rows(part).cpu().numpy()[: self.state_size]
+
+    def table_checksum(self) -> int:
+        """Order-free 64-bit checksum of the whole table (sum of the cells' bit patterns times a position hash), reduced
+        over the ranks on the device: equal tables <=> equal checksums for all practical purposes (collective)."""
+        torch = _torch()
+        part = torch.from_numpy(self._download()[0].copy()).to(self.dev)
+        idx = torch.arange(self.lo * self.action_size, self.lo * self.action_size + part.numel(), dtype=torch.int64, device=self.dev)
+        mix = (idx * 0x1E3779B97F4A7C15 + 0x7F4A7C15) & 0x7FFFFFFFFFFFFFFF
+        acc = (part.reshape(-1).view(torch.int32).to(torch.int64) * (mix | 1)).sum().reshape(1)
+        self.tp.all_reduce_sum_(acc)
+        return int(acc.item()) & 0xFFFFFFFFFFFFFFFF
 
 
 # ----------------------------------------------------------------------------------------------------- replicated table

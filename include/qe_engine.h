@@ -49,6 +49,7 @@ typedef struct qe_engine qe_engine_t;
 int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, int32_t device, qe_engine_t** out);
 int qe_destroy(qe_engine_t* e);
 const char* qe_last_error(void);
+int qe_set_last_error(int code, const char* msg); /* internal: sets the thread-local message, returns code */
 int qe_set_discount(qe_engine_t* e, float discount_factor);
 /* fp32 table in HBM, row-major with a padded row stride (in floats); rows are 16-byte aligned */
 float* qe_table_ptr(qe_engine_t* e);
@@ -188,16 +189,42 @@ int qe_table_import_dense(qe_engine_t* e, const float* dense, void* stream);
 int qe_table_delta_dense(qe_engine_t* e, const float* base, float* delta_out, void* stream);
 int qe_table_merge_dense(qe_engine_t* e, float* base_inout, const float* delta_sum, void* stream);
 
+/* ---- sharded table over peer memory (BASELINE config 4; round 2) -------------------------------------------------
+ * Replaces what the reference's MPI trainer does with one table on rank 0 and transitions shipped to it
+ * (q_learning_async_dist.py:59-281) by a state-range-sharded table: rank g owns the states [g * rows, (g + 1) * rows),
+ * rows = ceil(S / G); agent i lives on rank i / ceil(N / G) for good.  Every rank runs ONE persistent kernel; rows,
+ * writer records and targets travel as peer loads / stores over NVLink, phases are separated by flag barriers in peer
+ * memory (no NCCL call on the data path; see csrc/qe_shard.cuh).  Hash MDP only.  Results (table, states, returns) are
+ * identical to the single-GPU engine and to the reference's sequential loop in global agent order.
+ * One process per GPU: create, exchange qe_shard_ipc_handle() with the peers (64 bytes), qe_shard_connect_ipc() each,
+ * then qe_shard_steps(&mine, 1, ...) collectively.  All ranks in one process on one GPU (tests): qe_shard_connect_local()
+ * and ONE call qe_shard_steps(all, G, ...). */
+typedef struct qe_shard qe_shard_t;
+int qe_shard_create(int64_t num_states, int32_t num_actions, float discount_factor, int32_t device, int32_t rank, int32_t world,
+                    int32_t num_agents, uint32_t env_seed, qe_shard_t** out);
+int qe_shard_destroy(qe_shard_t* s);
+int qe_shard_ipc_handle(qe_shard_t* s, void* out64);
+int qe_shard_connect_ipc(qe_shard_t* s, int32_t peer_rank, const void* handle64);
+int qe_shard_connect_local(qe_shard_t* s, int32_t peer_rank, qe_shard_t* peer);
+int qe_shard_fill_random(qe_shard_t* s, uint32_t seed, void* stream);            /* this rank's slice of qe_table_fill_random */
+int qe_shard_reset(qe_shard_t* s, uint32_t stream_seed, uint32_t t_init, void* stream); /* initial states of its agents (qe_mdp_reset by global id) */
+int qe_shard_steps(qe_shard_t* const* ranks, int32_t nlocal, int32_t steps, const uint64_t* explore_thresholds_host,
+                   const float* learning_rates_host, uint32_t stream_seed, uint32_t env_stream_seed, int32_t empty_all, int32_t use_masks,
+                   uint64_t term_threshold, void* stream);
+int qe_shard_sync(qe_shard_t* s, void* stream);
+int qe_shard_download(qe_shard_t* s, float* table_host, int32_t* states_host, float* returns_host, double* episode_sum, uint64_t* episode_count);
+int qe_shard_rows_host(qe_shard_t* s, const int64_t* states_host, float* out_host, int32_t n);
+int32_t qe_shard_info(qe_shard_t* s, int32_t what); /* 0: rows per shard, 1: agents per rank (ceil), 2: agents of this rank, 3: kernels launched */
+
 /* introspection for benchmarks / tests */
 uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k);
 int64_t qe_kernel_launches(qe_engine_t* e);     /* kernels launched by this handle so far */
 int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch */
-/* form of the TD update the last fused launch used: 0 = writer lists, 1 = per-step sort (both exact; the engine times
- * its launches and keeps the faster one; QE_SORTED=0/1 in the environment pins it) */
+/* form of the TD update the last fused launch used: 0 = writer lists, 1 = per-step sort, 3 = target pipeline (all exact) */
 int32_t qe_fused_form(qe_engine_t* e);
-/* Which exact form of the TD update the fused loop uses: 0 = writer lists, 1 = per-step sort, 2 = keep timing both and
- * use the faster one (default; the QE_SORTED environment variable sets the initial value).  Both forms give identical
- * results.  The replicated multi-GPU mode pins form 1 on every rank: merged replicas learn G times as fast, agents herd
+/* Which exact form of the TD update the fused loop uses: 0 = writer lists, 1 = per-step sort, 2 = keep timing those two
+ * and use the faster one, 3 = target pipeline (csrc/qe_pipe.cuh; default; QE_FORM in the environment sets the initial
+ * value).  All forms give identical results.  The replicated multi-GPU mode pins form 1 on every rank: merged replicas learn G times as fast, agents herd
  * sooner, and ranks that probe at different moments would wait for each other at the all-reduce. */
 int qe_set_fused_form(qe_engine_t* e, int32_t form);
 /* phase clock of the last fused launch (synchronous): out_host[0] = %globaltimer (ns) at kernel start, then for each

@@ -55,10 +55,11 @@ def main() -> int:
             res = co.run(co.ENV_MDP, q_o, None, st_o, mk_o, num_states=S, env_seed=env_seed, term_thresh=tt, uniforms=None, slots=4,
                          stream_seed=seed, steps=steps, eps_thresh=th, lr=lr, gamma=GAMMA, empty_all=A > 10, agent_rewards=rew)
             good = res["rc"] == 0 and np.array_equal(states, st_o) and np.array_equal(table, q_o) and np.array_equal(rets, rew)
-            print(f"sharded G={tp.world_size} S={S} A={A} N={N} steps={steps}: rounds={sh.rounds_total} "
+            print(f"sharded G={tp.world_size} S={S} A={A} N={N} steps={steps}: "
                   f"states_equal={np.array_equal(states, st_o)} table_equal={np.array_equal(table, q_o)} returns_equal={np.array_equal(rets, rew)}",
                   flush=True)
             ok = ok and good
+        sh.close()
         del sh
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -1,7 +1,8 @@
 """Multi-GPU modes on ONE device: G virtual ranks (threads, LoopbackTransport) share the GPU.
 
 Sharded table (SURVEY 8e / BASELINE config 4): table, agent states and running returns after K vector steps must be
-identical -- bit for bit -- to the single-GPU fused loop AND to the C oracle on the same seeds, for any G.
+identical -- bit for bit -- to the single-GPU fused loop AND to the C oracle on the same seeds, for any G.  The G ranks
+run side by side in ONE cooperative launch of the peer-memory kernel (csrc/qe_shard.cuh), a group of CTAs per rank.
 Replicated table (config 5): the merged table must equal the NumPy restatement of the delta rule applied to the
 oracle's per-rank tables (exact at G = 2: a two-term sum is order-free)."""
 import ctypes as C
@@ -56,7 +57,8 @@ def _random_table(S, A, table_seed):
 
 
 @pytest.mark.parametrize("world,S,A,N,steps", [(2, 5000, 8, 6000, 10), (3, 1000, 16, 4000, 8), (4, 200_000, 8, 30_000, 6),
-                                               (2, 64, 4, 512, 6)])
+                                               (2, 64, 4, 512, 6), (8, 30_000, 8, 100_000, 12), (8, 7, 20, 3000, 5),
+                                               (5, 1_000_000, 16, 200_001, 9)])
 def test_sharded_table_matches_oracle(capi, world, S, A, N, steps):
     from dist_classicrl_b200 import distributed as D
     from dist_classicrl_b200.schedules import ConstantSchedule
@@ -72,18 +74,17 @@ def test_sharded_table_matches_oracle(capi, world, S, A, N, steps):
         sh.run_steps(steps, ConstantSchedule(EPS), ConstantSchedule(LR))
         table = sh.gather_table()
         states, rets = sh.gather_agents()
-        return table, states, rets, sh.rounds_total, sh.episode_count
+        cs = sh.table_checksum()
+        sh.close()
+        return table, states, rets, cs
 
     out = D.run_loopback(world, body)
-    table, states, rets, rounds, _ = out[0]
+    table, states, rets, cs = out[0]
     assert np.array_equal(states, st_o)
     assert np.array_equal(table, q_o), f"max |dq| = {np.abs(table - q_o).max()}"
     assert np.array_equal(rets, rew_o)
-    assert rounds >= steps  # at least one exact local update per step
-    if N >= S // 4:
-        assert rounds > steps, "this density must need more than one round somewhere (cross-shard hazards)"
     for other in out[1:]:
-        assert np.array_equal(other[0], table)
+        assert np.array_equal(other[0], table) and other[3] == cs
 
 
 @pytest.mark.parametrize("stepwise", [False, True])
