@@ -42,7 +42,9 @@ SIGNATURES = {
     "qe_destroy": (C.c_int, [vp]),
     "qe_last_error": (C.c_char_p, []),
     "qe_set_last_error": (C.c_int, [C.c_int, C.c_char_p]),
-    "qe_shard_create": (C.c_int, [i64, i32, f32, i32, i32, i32, i32, u32, C.POINTER(vp)]),
+    "qe_shard_slab_bytes": (i64, [i64, i32, i32, i32]),
+    "qe_shard_create": (C.c_int, [i64, i32, f32, i32, i32, i32, i32, u32, vp, C.POINTER(vp)]),
+    "qe_shard_connect_ptr": (C.c_int, [vp, i32, vp]),
     "qe_shard_destroy": (C.c_int, [vp]),
     "qe_shard_ipc_handle": (C.c_int, [vp, vp]),
     "qe_shard_connect_ipc": (C.c_int, [vp, i32, vp]),
@@ -53,6 +55,8 @@ SIGNATURES = {
     "qe_shard_sync": (C.c_int, [vp, vp]),
     "qe_shard_download": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "qe_shard_rows_host": (C.c_int, [vp, vp, vp, i32]),
+    "qe_shard_phase_ns": (C.c_int, [vp, vp]),
+    "qe_shard_probe": (C.c_double, [vp, i32, i32]),
     "qe_shard_info": (i32, [vp, i32]),
     "qe_set_discount": (C.c_int, [vp, f32]),
     "qe_table_ptr": (vp, [vp]),

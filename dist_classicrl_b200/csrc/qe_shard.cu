@@ -33,7 +33,8 @@ struct qe_shard {
     int n_total = 0, n_home = 0, nh = 0;
     float gamma = 0.0f;
     uint32_t env_seed = 0;
-    char* slab = nullptr;       // the shared part (one allocation, one IPC handle)
+    char* slab = nullptr;       // the shared part (one allocation: one IPC handle, or the caller's symmetric memory)
+    bool slab_external = false;
     size_t slab_bytes = 0;
     size_t off_q = 0, off_rec = 0, off_seg = 0, off_inbox = 0, off_pos = 0, off_tw = 0, off_cin = 0, off_flag = 0;
     char* peer_slab[kMaxRanks] = {};   // every rank's slab as mapped here (own: slab)
@@ -83,10 +84,72 @@ __global__ void shard_rows_kernel(const float* q, int ld, int A, const int64_t* 
     }
 }
 
+// development aid: random 32-byte loads (mode 0) or 8-byte stores (mode 1) over a rank's table shard as mapped here
+__global__ void __launch_bounds__(256) shard_probe_kernel(float* buf, uint32_t rows, int per_thread, uint32_t seed, int mode, float* out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    for (int it = 0; it < per_thread; ++it) {
+        const uint32_t r = __umulhi(fmix32((tid * 7919u + (uint32_t)it) ^ seed), rows);
+        float* p = buf + (size_t)r * 8;
+        if (mode == 0) { const F8 v = ld_row8(p); acc += v.v[0] + v.v[7]; }
+        else *reinterpret_cast<uint2*>(p) = make_uint2(tid, (uint32_t)it);
+    }
+    if (acc == 12345.678f) out[0] = acc;
+}
+
+static size_t shard_layout(qe_shard* s) {
+    size_t o = 0;
+    s->off_q = o; o += al256(sizeof(float) * (size_t)s->rows * s->ld);
+    s->off_rec = o; o += al256(sizeof(uint2) * ((size_t)s->n_total + 8));
+    s->off_seg = o; o += al256(sizeof(uint2) * (size_t)s->rows);
+    s->off_inbox = o; o += al256(sizeof(int2) * (size_t)s->n_total);
+    s->off_pos = o; o += al256(sizeof(int32_t) * (size_t)s->n_home);
+    s->off_tw = o; o += al256(sizeof(uint4) * (size_t)s->n_home);
+    s->off_cin = o; o += al256(sizeof(unsigned int) * kMaxRanks);
+    s->off_flag = o; o += al256(sizeof(unsigned int) * kMaxRanks);
+    return o;
+}
+
 extern "C" {
 
+/* bytes of the slab every rank shares with its peers (the same on every rank) */
+int64_t qe_shard_slab_bytes(int64_t num_states, int32_t num_actions, int32_t world, int32_t num_agents) {
+    if (num_states <= 0 || num_actions <= 0 || num_actions > 32 || world < 1 || num_agents <= 0) return -1;
+    qe_shard t;
+    t.lpr = num_actions <= 8 ? 1 : (num_actions <= 16 ? 2 : 4);
+    t.ld = 8 * t.lpr;
+    t.rows = (num_states + world - 1) / world;
+    t.n_total = num_agents;
+    t.n_home = (num_agents + world - 1) / world;
+    return (int64_t)shard_layout(&t);
+}
+
+/* development aid: G random accesses per second over the table shard of `peer_rank` (its first `rows` rows of 32 bytes) */
+double qe_shard_probe(qe_shard_t* s, int32_t peer_rank, int32_t mode) {
+    if (cudaSetDevice(s->device) != cudaSuccess || !s->peer_slab[peer_rank]) return -1.0;
+    float* buf = (float*)(s->peer_slab[peer_rank] + s->off_q);
+    const uint32_t rows = (uint32_t)std::min<int64_t>(s->rows * s->ld / 8, 1ll << 30);
+    float* out = nullptr;
+    if (cudaMalloc(&out, 256) != cudaSuccess) return -1.0;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    const int blocks = s->sms * 3, per = 32;
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(a);
+        shard_probe_kernel<<<blocks, 256>>>(buf, rows, per, 17u + r, mode, out);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    cudaFree(out);
+    return (double)blocks * 256 * per / best / 1e6;
+}
+
 int qe_shard_create(int64_t num_states, int32_t num_actions, float discount_factor, int32_t device, int32_t rank, int32_t world,
-                    int32_t num_agents, uint32_t env_seed, qe_shard_t** out) {
+                    int32_t num_agents, uint32_t env_seed, void* external_slab, qe_shard_t** out) {
     if (!out || num_states <= 0 || num_actions <= 0 || num_actions > 32) return sfail(QE_ERR_ARG, "sharded table: 1 <= actions <= 32");
     if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return sfail(QE_ERR_ARG, "sharded table: 1 <= world <= %d", kMaxRanks);
     if (num_agents <= 0 || num_agents >= (1 << 24)) return sfail(QE_ERR_ARG, "num_agents must be in [1, 2^24)");
@@ -108,17 +171,14 @@ int qe_shard_create(int64_t num_states, int32_t num_actions, float discount_fact
     cudaDeviceProp prop;
     SCK(cudaGetDeviceProperties(&prop, device));
     s->sms = prop.multiProcessorCount;
-    size_t o = 0;
-    s->off_q = o; o += al256(sizeof(float) * (size_t)s->rows * s->ld);
-    s->off_rec = o; o += al256(sizeof(uint2) * ((size_t)num_agents + 8));
-    s->off_seg = o; o += al256(sizeof(uint2) * (size_t)s->rows);
-    s->off_inbox = o; o += al256(sizeof(int2) * (size_t)num_agents);
-    s->off_pos = o; o += al256(sizeof(int32_t) * (size_t)s->n_home);
-    s->off_tw = o; o += al256(sizeof(uint4) * (size_t)s->n_home);
-    s->off_cin = o; o += al256(sizeof(unsigned int) * kMaxRanks);
-    s->off_flag = o; o += al256(sizeof(unsigned int) * kMaxRanks);
+    const size_t o = shard_layout(s);
     s->slab_bytes = o;
-    SCK(cudaMalloc(&s->slab, o));
+    if (external_slab) {  // device memory the caller shares with the peers itself (symmetric memory: large pages over NVLink)
+        s->slab = (char*)external_slab;
+        s->slab_external = true;
+    } else {
+        SCK(cudaMalloc(&s->slab, o));
+    }
     SCK(cudaMemset(s->slab, 0, o));
     SCK(cudaMemset(s->slab + s->off_rec, 0xFF, sizeof(uint2) * ((size_t)num_agents + 8)));
     s->peer_slab[rank] = s->slab;
@@ -138,6 +198,8 @@ int qe_shard_create(int64_t num_states, int32_t num_actions, float discount_fact
     SCK(cudaMemset(L.ep_count, 0, sizeof(unsigned long long)));
     SCK(cudaMalloc(&L.err, sizeof(int)));
     SCK(cudaMemset(L.err, 0, sizeof(int)));
+    SCK(cudaMalloc(&L.phase_ns, 128 * sizeof(unsigned long long)));
+    SCK(cudaMemset(L.phase_ns, 0, 128 * sizeof(unsigned long long)));
     *out = s;
     return QE_OK;
 }
@@ -148,16 +210,17 @@ int qe_shard_destroy(qe_shard_t* s) {
     cudaDeviceSynchronize();
     for (int g = 0; g < kMaxRanks; ++g)
         if (s->peer_ipc[g] && s->peer_slab[g]) cudaIpcCloseMemHandle(s->peer_slab[g]);
-    cudaFree(s->slab);
+    if (!s->slab_external) cudaFree(s->slab);
     ShardLocal& L = s->L;
     cudaFree(L.st_a); cudaFree(L.st_b); cudaFree(L.ep_ret); cudaFree(L.kv[0]); cudaFree(L.kv[1]); cudaFree(L.ghist); cudaFree(L.rowtot);
-    cudaFree(L.wcnt); cudaFree(L.ctr); cudaFree(L.ep_sum); cudaFree(L.ep_count); cudaFree(L.err); cudaFree(s->d_thresh); cudaFree(s->d_lr);
+    cudaFree(L.wcnt); cudaFree(L.ctr); cudaFree(L.phase_ns); cudaFree(L.ep_sum); cudaFree(L.ep_count); cudaFree(L.err); cudaFree(s->d_thresh); cudaFree(s->d_lr);
     delete s;
     return QE_OK;
 }
 
 /* the CUDA IPC handle (64 bytes) of this rank's slab, to be opened by the other processes */
 int qe_shard_ipc_handle(qe_shard_t* s, void* out64) {
+    if (s->slab_external) return sfail(QE_ERR_ARG, "the slab belongs to the caller: share it the way it was allocated");
     SCK(cudaSetDevice(s->device));
     cudaIpcMemHandle_t h;
     SCK(cudaIpcGetMemHandle(&h, s->slab));
@@ -174,6 +237,13 @@ int qe_shard_connect_ipc(qe_shard_t* s, int32_t peer_rank, const void* handle64)
     SCK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     s->peer_slab[peer_rank] = (char*)p;
     s->peer_ipc[peer_rank] = true;
+    return QE_OK;
+}
+/* the peer's slab as the caller mapped it (symmetric memory) */
+int qe_shard_connect_ptr(qe_shard_t* s, int32_t peer_rank, void* peer_slab) {
+    if (peer_rank < 0 || peer_rank >= s->world || !peer_slab) return sfail(QE_ERR_ARG, "bad peer rank %d", peer_rank);
+    s->peer_slab[peer_rank] = (char*)peer_slab;
+    s->peer_ipc[peer_rank] = false;
     return QE_OK;
 }
 /* ranks that share a process (and a device): plain pointers */
@@ -335,6 +405,14 @@ int qe_shard_rows_host(qe_shard_t* s, const int64_t* states_host, float* out_hos
     SCK(cudaGetLastError());
     SCK(cudaMemcpy(out_host, d_out, sizeof(float) * (size_t)n * s->A, cudaMemcpyDeviceToHost));
     cudaFree(d_rows); cudaFree(d_out);
+    return QE_OK;
+}
+/* phase clock of the last launch (synchronous): out_host[8 * k + j], j = 0: start of vector step k, 7: end of this rank's phase A
+ * work, 1: after phase A's barrier, 2: after phase T, 3: after phase C, 4 / 5 / 6: after the three stages of the distributed sort
+ * (partition counts, scatter into the owners' inboxes, local sort + bounds); k < 16; %globaltimer ns */
+int qe_shard_phase_ns(qe_shard_t* s, uint64_t* out_host128) {
+    SCK(cudaSetDevice(s->device));
+    SCK(cudaMemcpy(out_host128, s->L.phase_ns, 128 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return QE_OK;
 }
 int32_t qe_shard_info(qe_shard_t* s, int32_t what) {  /* 0: rows per shard, 1: agents per rank (ceil), 2: agents of this rank, 3: kernels launched */

@@ -27,7 +27,7 @@
 namespace qe {
 
 constexpr int kMaxRanks = 8;
-constexpr uint64_t kShardTimeoutNs = 8000000000ull;
+constexpr uint64_t kShardTimeoutNs = 20000000000ull;
 
 struct ShardPeer {           // what rank g exposes to every rank (pointers into its slab, valid in THIS process)
     float* q;                // [rows][ld] table shard
@@ -51,6 +51,7 @@ struct ShardLocal {          // private to a rank
     double* ep_sum;
     unsigned long long* ep_count;
     int* err;
+    unsigned long long* phase_ns;  // [8 * 16] %globaltimer after {A, T, C, partition counts, scatter, local sort} of the first 16 steps
 };
 struct ShardArgs {
     int G, first_rank, nlocal, blocks_per_rank, multi_device;
@@ -325,6 +326,10 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
     uint32_t epoch = H.epoch0;
     int n_in = (int)ld_relaxed_u32(L.ctr + 1);  // records at this owner in the current order
     int old_n = n_in;
+    int kstep = -1;
+    auto stamp = [&](int slot) {
+        if (rtid == 0 && kstep >= 0 && kstep < 16) L.phase_ns[8 * kstep + slot] = global_ns();
+    };
 
     // -------- the distributed stable sort of the agents by the states in `keys` (next states, or the initial ones)
     auto sort_step = [&](const int32_t* keys) {
@@ -358,6 +363,7 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
             if (lane == 0) H.peer[d].cin[me] = carry;
         }
         shard_xsync(grid, H, epoch);
+        stamp(4);
         // S3: where my pairs start at every owner, how many pairs I receive, then the stable scatter into the inboxes
         if (threadIdx.x < G) {
             unsigned int off = 0;
@@ -387,17 +393,21 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
             }
         }
         shard_xsync(grid, H, epoch);
+        stamp(5);
         // S4 + S5: the owner's local sort, positions to the home ranks, segment bounds
         const int src = shard_sort<WARPS>(grid, s_whist, s_base, s_wsum, n_in, old_n, H, L, me, b, nb);
         shard_bounds<WARPS>(L.kv[src], n_in, own.seg, b, nb);
         old_n = n_in;
         if (rtid == 0) L.ctr[1] = (unsigned int)n_in;
         shard_xsync(grid, H, epoch);
+        stamp(6);
     };
 
     if (!H.sorted_valid) sort_step(L.st_a);
 
     for (int k = 0; k < H.steps; ++k) {
+        kstep = k;
+        stamp(0);
         int32_t* cur = (k & 1) ? L.st_b : L.st_a;
         int32_t* nxt = (k & 1) ? L.st_a : L.st_b;
         const uint32_t t_sel = H.t0 + (uint32_t)k, t_env = H.env_t0 + (uint32_t)k;
@@ -457,7 +467,9 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
             __syncthreads();
         }
         if (rtid == 0) L.ctr[0] = 0u;
+        stamp(7);
         shard_xsync(grid, H, epoch);
+        stamp(1);
 
         // ---------------- phase T: in-order target pipeline over the home agents (qe_pipe.cuh), rows / records / targets
         // through peer pointers
@@ -590,6 +602,7 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
             }
         }
         shard_xsync(grid, H, epoch);
+        stamp(2);
 
         // ---------------- phase C: every owner commits the records it holds (as in qe_pipe.cuh)
         {
@@ -667,6 +680,7 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
             }
         }
         __syncthreads();
+        stamp(3);
 
         // ---------------- phase S: the next step's order
         sort_step(nxt);

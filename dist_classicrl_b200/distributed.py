@@ -323,8 +323,29 @@ class ShardedQLearning:
         self.lo, self.hi = shard_range(state_size, self.world, self.rank)
         self._lib = capi.lib()
         self._h = C.c_void_p()
+        # The slab the peers read and write: torch symmetric memory (CUDA VMM, large pages, file descriptors exchanged by
+        # torch) when the ranks are processes; CUDA IPC of a cudaMalloc block as the fallback (30x slower for random peer
+        # accesses: QE_SHARD_IPC=1 forces it, for the record)
+        self._symm = None
+        slab = None
+        if isinstance(transport, TorchDistTransport) and self.world > 1 and os.environ.get("QE_SHARD_IPC", "0") != "1":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                nbytes = int(self._lib.qe_shard_slab_bytes(self.state_size, self.action_size, self.world, self.num_agents))
+                buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.dev)
+                import torch.distributed as dist
+
+                hdl = symm_mem.rendezvous(buf, transport.group if transport.group is not None else dist.group.WORLD)
+                self._symm = (buf, hdl)
+                slab = C.c_void_p(int(buf.data_ptr()))
+            except Exception as exc:  # noqa: BLE001
+                import warnings
+
+                warnings.warn(f"torch symmetric memory is unavailable ({exc!r}): the sharded table falls back to CUDA IPC mappings (slow peer access)")
+                self._symm = None
         capi.check(self._lib.qe_shard_create(self.state_size, self.action_size, self.discount_factor, self.device_index, self.rank,
-                                             self.world, self.num_agents, self.env_seed, C.byref(self._h)))
+                                             self.world, self.num_agents, self.env_seed, slab, C.byref(self._h)))
         self.n_home = int(self._lib.qe_shard_info(self._h, 1))
         self.n_here = int(self._lib.qe_shard_info(self._h, 2))
         self._peers: list | None = None  # loopback: every rank's handle (rank 0 launches for all of them)
@@ -346,6 +367,13 @@ class ShardedQLearning:
             return
         import torch.distributed as dist
 
+        if self._symm is not None:
+            ptrs = list(self._symm[1].buffer_ptrs)
+            for g in range(self.world):
+                if g != self.rank:
+                    capi.check(lib.qe_shard_connect_ptr(self._h, g, C.c_void_p(int(ptrs[g]))))
+            self.tp.barrier()
+            return
         buf = (C.c_ubyte * 64)()
         capi.check(lib.qe_shard_ipc_handle(self._h, buf))
         mine = bytes(buf)
@@ -373,6 +401,7 @@ class ShardedQLearning:
         if h:
             self._lib.qe_shard_destroy(h)
         self.tp.barrier()
+        self._symm = None
 
     # -- helpers
     def _stream(self):
@@ -422,6 +451,17 @@ class ShardedQLearning:
                 exploration_rate_schedule.update(self.num_agents)
             self._launch(th, lrs)
             done += k
+
+    def phase_us(self, steps: int = 8) -> dict:
+        """Per-phase microseconds of the last launch on THIS rank (mean over its first ``steps`` vector steps)."""
+        buf = (C.c_uint64 * 128)()
+        self.sync()
+        capi.check(self._lib.qe_shard_phase_ns(self._h, buf))
+        k = max(1, min(int(steps), 16, self.launch_steps))
+        t = np.asarray(list(buf), dtype=np.float64).reshape(16, 8)[:k]
+        d = lambda a, b: float(np.mean(t[:, a] - t[:, b]) / 1e3)  # noqa: E731
+        return {"A_work": d(7, 0), "A_barrier": d(1, 7), "T": d(2, 1), "C": d(3, 2), "sort_counts": d(4, 3), "sort_scatter": d(5, 4),
+                "sort_local": d(6, 5), "step": d(6, 0)}
 
     def sync(self) -> None:
         """Wait for this rank's kernels and raise deferred device errors."""

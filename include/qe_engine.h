@@ -200,8 +200,14 @@ int qe_table_merge_dense(qe_engine_t* e, float* base_inout, const float* delta_s
  * then qe_shard_steps(&mine, 1, ...) collectively.  All ranks in one process on one GPU (tests): qe_shard_connect_local()
  * and ONE call qe_shard_steps(all, G, ...). */
 typedef struct qe_shard qe_shard_t;
+/* external_slab: NULL (the library allocates the shared slab with cudaMalloc; peers map it with CUDA IPC) or
+ * qe_shard_slab_bytes() of device memory the caller has made visible to the peers itself -- e.g. torch symmetric memory
+ * (CUDA VMM, 2 MB pages): random peer accesses through a CUDA IPC mapping of a cudaMalloc block were measured at
+ * 0.23 G/s on B200 NVLink against 6.8 G/s through a large-page mapping (profiles/r2_p2p_microbench.md). */
+int64_t qe_shard_slab_bytes(int64_t num_states, int32_t num_actions, int32_t world, int32_t num_agents);
 int qe_shard_create(int64_t num_states, int32_t num_actions, float discount_factor, int32_t device, int32_t rank, int32_t world,
-                    int32_t num_agents, uint32_t env_seed, qe_shard_t** out);
+                    int32_t num_agents, uint32_t env_seed, void* external_slab, qe_shard_t** out);
+int qe_shard_connect_ptr(qe_shard_t* s, int32_t peer_rank, void* peer_slab);
 int qe_shard_destroy(qe_shard_t* s);
 int qe_shard_ipc_handle(qe_shard_t* s, void* out64);
 int qe_shard_connect_ipc(qe_shard_t* s, int32_t peer_rank, const void* handle64);
@@ -214,6 +220,8 @@ int qe_shard_steps(qe_shard_t* const* ranks, int32_t nlocal, int32_t steps, cons
 int qe_shard_sync(qe_shard_t* s, void* stream);
 int qe_shard_download(qe_shard_t* s, float* table_host, int32_t* states_host, float* returns_host, double* episode_sum, uint64_t* episode_count);
 int qe_shard_rows_host(qe_shard_t* s, const int64_t* states_host, float* out_host, int32_t n);
+int qe_shard_phase_ns(qe_shard_t* s, uint64_t* out_host128); /* phase clock of the last launch, see csrc/qe_shard.cu */
+double qe_shard_probe(qe_shard_t* s, int32_t peer_rank, int32_t mode); /* development aid: G random 32-byte loads (0) / 8-byte stores (1) per second over a rank's shard as mapped here */
 int32_t qe_shard_info(qe_shard_t* s, int32_t what); /* 0: rows per shard, 1: agents per rank (ceil), 2: agents of this rank, 3: kernels launched */
 
 /* introspection for benchmarks / tests */
