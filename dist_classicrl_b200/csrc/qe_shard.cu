@@ -213,7 +213,7 @@ int qe_shard_destroy(qe_shard_t* s) {
     if (!s->slab_external) cudaFree(s->slab);
     ShardLocal& L = s->L;
     cudaFree(L.st_a); cudaFree(L.st_b); cudaFree(L.ep_ret); cudaFree(L.kv[0]); cudaFree(L.kv[1]); cudaFree(L.ghist); cudaFree(L.rowtot);
-    cudaFree(L.wcnt); cudaFree(L.ctr); cudaFree(L.phase_ns); cudaFree(L.ep_sum); cudaFree(L.ep_count); cudaFree(L.err); cudaFree(s->d_thresh); cudaFree(s->d_lr);
+    cudaFree(L.wcnt); cudaFree(L.bcnt); cudaFree(L.ctr); cudaFree(L.phase_ns); cudaFree(L.ep_sum); cudaFree(L.ep_count); cudaFree(L.err); cudaFree(s->d_thresh); cudaFree(s->d_lr);
     delete s;
     return QE_OK;
 }
@@ -331,10 +331,11 @@ int qe_shard_steps(qe_shard_t* const* ranks, int32_t nlocal, int32_t steps, cons
         if (s->sorted_valid != s0->sorted_valid || s->t != s0->t || s->epoch != s0->epoch) return sfail(QE_ERR_ARG, "qe_shard_steps: the local ranks are out of step");
         if (bpr > s->ghist_blocks) {
             SCK(cudaDeviceSynchronize());
-            cudaFree(s->L.ghist); cudaFree(s->L.wcnt);
-            s->L.ghist = nullptr; s->L.wcnt = nullptr;
+            cudaFree(s->L.ghist); cudaFree(s->L.wcnt); cudaFree(s->L.bcnt);
+            s->L.ghist = nullptr; s->L.wcnt = nullptr; s->L.bcnt = nullptr;
             SCK(cudaMalloc(&s->L.ghist, sizeof(int) * kRadix * (size_t)bpr));
             SCK(cudaMalloc(&s->L.wcnt, sizeof(unsigned int) * (size_t)warps_per_rank * kMaxRanks));
+            SCK(cudaMalloc(&s->L.bcnt, sizeof(unsigned int) * (size_t)bpr * kMaxRanks));
             s->ghist_blocks = bpr;
         }
         SCK(cudaMemsetAsync(s->L.ctr + 4, 0, sizeof(unsigned int), st));
@@ -342,8 +343,8 @@ int qe_shard_steps(qe_shard_t* const* ranks, int32_t nlocal, int32_t steps, cons
     }
     void* args[] = {&H};
     SCK(cudaLaunchCooperativeKernel(kern, dim3(bpr * nlocal), dim3(256), args, smem, st));
-    // barriers over all ranks in this launch: 3 per sort, 2 more per step
-    const uint32_t xs = (s0->sorted_valid ? 0u : 3u) + 5u * (uint32_t)steps;
+    // barriers over all ranks in this launch: 3 for the initial order, 3 per step
+    const uint32_t xs = (s0->sorted_valid ? 0u : 3u) + 3u * (uint32_t)steps;
     for (int v = 0; v < nlocal; ++v) {
         qe_shard* s = ranks[v];
         if (H.multi_device) s->epoch += xs;
@@ -408,8 +409,8 @@ int qe_shard_rows_host(qe_shard_t* s, const int64_t* states_host, float* out_hos
     return QE_OK;
 }
 /* phase clock of the last launch (synchronous): out_host[8 * k + j], j = 0: start of vector step k, 7: end of this rank's phase A
- * work, 1: after phase A's barrier, 2: after phase T, 3: after phase C, 4 / 5 / 6: after the three stages of the distributed sort
- * (partition counts, scatter into the owners' inboxes, local sort + bounds); k < 16; %globaltimer ns */
+ * work, 1: after the barrier over all ranks that follows it, 4: after the scatter of the next order's pairs into the owners'
+ * inboxes, 2: after phase T and its barrier, 3: after phase C, 6: after the local sort and its barrier; k < 16; %globaltimer ns */
 int qe_shard_phase_ns(qe_shard_t* s, uint64_t* out_host128) {
     SCK(cudaSetDevice(s->device));
     SCK(cudaMemcpy(out_host128, s->L.phase_ns, 128 * sizeof(uint64_t), cudaMemcpyDeviceToHost));

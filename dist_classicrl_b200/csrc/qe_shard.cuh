@@ -46,7 +46,8 @@ struct ShardLocal {          // private to a rank
     int2* kv[2];             // [N] radix ping-pong
     int* ghist;              // [kRadix][blocks per rank]
     int* rowtot;             // [kRadix]
-    unsigned int* wcnt;      // [warps per rank][G] pairs per (warp, destination), scanned in place
+    unsigned int* wcnt;      // [warps per rank][G] pairs per (warp, destination) before this warp inside its block
+    unsigned int* bcnt;      // [blocks per rank][G] pairs per (block, destination), scanned in place over the blocks
     unsigned int* ctr;       // [16] 0: chunk claims of phase T; 1: agents in the order kv[] / seg[] still describe; 4: abort flag
     double* ep_sum;
     unsigned long long* ep_count;
@@ -325,85 +326,151 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
     const int64_t rows = H.rows;
     uint32_t epoch = H.epoch0;
     int n_in = (int)ld_relaxed_u32(L.ctr + 1);  // records at this owner in the current order
-    int old_n = n_in;
+    int old_n = n_in, n_next = n_in;
     int kstep = -1;
     auto stamp = [&](int slot) {
         if (rtid == 0 && kstep >= 0 && kstep < 16) L.phase_ns[8 * kstep + slot] = global_ns();
     };
 
-    // -------- the distributed stable sort of the agents by the states in `keys` (next states, or the initial ones)
-    auto sort_step = [&](const int32_t* keys) {
-        // S1: pairs per (warp, destination); every warp owns a contiguous part of the home agents
-        const int per = ((nh + rwarps - 1) / rwarps + 31) & ~31;
-        const int lo = min(rwarp * per, nh), hi = min(lo + per, nh);
-        {
-            unsigned int cnt = 0;  // lane d < G counts destination d
-            for (int base = lo; base < hi; base += 32) {
-                const int j = base + lane;
-                const int d = j < hi ? (int)(__ldcg(keys + j) / rows) : -1;
-                for (int g = 0; g < G; ++g) {
-                    const unsigned int c = __popc(__ballot_sync(kFull, d == g));
-                    if (lane == g) cnt += c;
-                }
-            }
-            if (lane < G) L.wcnt[(size_t)rwarp * G + lane] = cnt;
+    // -------- the distributed stable sort of the agents by state, in pieces.  Every warp owns the contiguous part
+    // [part_lo, part_hi) of the home agents (phase A walks the same parts, so it can count the destinations as it goes).
+    const int part = ((nh + rwarps - 1) / rwarps + 31) & ~31;
+    const int part_lo = min(rwarp * part, nh), part_hi = min(part_lo + part, nh);
+    __shared__ unsigned int s_wc[WARPS][kMaxRanks];
+    // destinations of one tile of keys -> per-lane counters (lane d < G counts destination d)
+    auto count_tile = [&](int d, unsigned int& cnt) {
+        for (int g = 0; g < G; ++g) {
+            const unsigned int c = __popc(__ballot_sync(kFull, d == g));
+            if (lane == g) cnt += c;
         }
-        grid.sync();
-        // S2: exclusive scan over the warps per destination (warp d of the group's first block), totals to the owners
+    };
+    // S1 (end): the warps' counters -> offsets inside the block (wcnt) and block totals (bcnt)
+    auto file_counts = [&](unsigned int cnt) {
+        if (lane < G) s_wc[warp][lane] = cnt;
+        __syncthreads();
+        if (threadIdx.x < G) {
+            unsigned int run = 0;
+            for (int w = 0; w < WARPS; ++w) {
+                L.wcnt[(size_t)(b * WARPS + w) * G + threadIdx.x] = run;
+                run += s_wc[w][threadIdx.x];
+            }
+            L.bcnt[(size_t)b * G + threadIdx.x] = run;
+        }
+        __syncthreads();
+    };
+    // S2 (after a grid barrier): exclusive scan of the block totals per destination (warp d of the group's first block),
+    // totals to the owners
+    auto scan_counts = [&]() {
         if (b == 0 && warp < G) {
             const int d = warp;
-            unsigned int carry = 0;
-            for (int x0 = 0; x0 < rwarps; x0 += 32) {
-                const int x = x0 + lane;
-                const unsigned int v = x < rwarps ? __ldcg(L.wcnt + (size_t)x * G + d) : 0u;
-                const unsigned int incl = (unsigned int)warp_incl_scan((int)v);
-                if (x < rwarps) L.wcnt[(size_t)x * G + d] = carry + incl - v;
-                carry += __shfl_sync(kFull, incl, 31);
+            const int per = (nb + 31) / 32;
+            unsigned int v[kScanPerLane];
+            unsigned int sum = 0;
+#pragma unroll
+            for (int j = 0; j < kScanPerLane; ++j) {
+                const int x = lane * per + j;
+                v[j] = (j < per && x < nb) ? __ldcg(L.bcnt + (size_t)x * G + d) : 0u;
+                sum += v[j];
             }
-            if (lane == 0) H.peer[d].cin[me] = carry;
+            const unsigned int incl = (unsigned int)warp_incl_scan((int)sum);
+            unsigned int run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < kScanPerLane; ++j) {
+                const int x = lane * per + j;
+                if (j < per && x < nb) L.bcnt[(size_t)x * G + d] = run;
+                run += v[j];
+            }
+            if (lane == 31) H.peer[d].cin[me] = incl;
         }
-        shard_xsync(grid, H, epoch);
-        stamp(4);
-        // S3: where my pairs start at every owner, how many pairs I receive, then the stable scatter into the inboxes
+    };
+    // S3 (after a barrier over all ranks): where my pairs start at every owner, how many pairs I receive, then the
+    // stable scatter of {state inside the shard, agent} into the owners' inboxes
+    auto scatter_pairs = [&](const int32_t* keys) {
         if (threadIdx.x < G) {
             unsigned int off = 0;
             for (int r = 0; r < me; ++r) off += ld_relaxed_sys_u32(H.peer[threadIdx.x].cin + r);
-            s_off[threadIdx.x] = off;
+            s_off[threadIdx.x] = off + __ldcg(L.bcnt + (size_t)b * G + threadIdx.x);
         }
         {
             unsigned int tot = 0;
             for (int r = 0; r < G; ++r) tot += ld_relaxed_sys_u32(own.cin + r);
-            n_in = (int)tot;
+            n_next = (int)tot;  // (the current order's records are still in use: n_in changes with the local sort)
         }
         __syncthreads();
-        {
-            unsigned int run = lane < G ? __ldcg(L.wcnt + (size_t)rwarp * G + lane) + s_off[lane] : 0u;  // lane d: next free slot at owner d
-            for (int base = lo; base < hi; base += 32) {
-                const int j = base + lane;
-                const int32_t k = j < hi ? __ldcg(keys + j) : 0;
-                const int d = j < hi ? (int)(k / rows) : -1;
-                unsigned int slot = 0;
-                for (int g = 0; g < G; ++g) {
-                    const uint32_t m = __ballot_sync(kFull, d == g);
-                    const unsigned int start = __shfl_sync(kFull, run, g);
-                    if (d == g) slot = start + __popc(m & ((1u << lane) - 1u));
-                    if (lane == g) run += __popc(m);
-                }
-                if (d >= 0) H.peer[d].inbox[slot] = make_int2((int32_t)(k - (int64_t)d * rows), home0 + j);
+        // Rounds of up to 256 agents per warp: the round's pairs are grouped by owner in shared memory first, so that the
+        // peer stores of consecutive lanes go to consecutive slots of one inbox (few large NVLink writes instead of one
+        // 8-byte write per pair: the fabric is bound by requests, not bytes).
+        unsigned int run = lane < G ? __ldcg(L.wcnt + (size_t)rwarp * G + lane) + s_off[lane] : 0u;  // lane d: next free slot at owner d
+        int2* stage = reinterpret_cast<int2*>(s_mem) + warp * 256;          // [256] pairs of the round, grouped by owner
+        unsigned int* sdst = reinterpret_cast<unsigned int*>(s_mem) + WARPS * 512 + warp * 256;  // [256] their global slots | owner << 28
+        constexpr int R = 8;
+        for (int base = part_lo; base < part_hi; base += 32 * R) {
+            int32_t kk[R];
+            int dd[R];
+            unsigned int cnt = 0;  // lane d: pairs of the round for owner d
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int j = base + 32 * u + lane;
+                kk[u] = j < part_hi ? __ldcg(keys + j) : 0;
+                dd[u] = j < part_hi ? (int)(kk[u] / rows) : -1;
+                count_tile(dd[u], cnt);
             }
+            const unsigned int incl = (unsigned int)warp_incl_scan((int)(lane < G ? cnt : 0u));
+            unsigned int lstart = incl - (lane < G ? cnt : 0u);  // lane d: first local slot of owner d in the stage
+            const unsigned int total = __shfl_sync(kFull, incl, 31);
+            unsigned int lrun = lstart;
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int j = base + 32 * u + lane;
+                unsigned int loc = 0, glob = 0;
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t m = __ballot_sync(kFull, dd[u] == g);
+                    const unsigned int ls = __shfl_sync(kFull, lrun, g), gs = __shfl_sync(kFull, run, g), l0 = __shfl_sync(kFull, lstart, g);
+                    if (dd[u] == g) {
+                        loc = ls + __popc(m & ((1u << lane) - 1u));
+                        glob = gs + (loc - l0);
+                    }
+                    if (lane == g) lrun += __popc(m);
+                }
+                if (dd[u] >= 0) {
+                    stage[loc] = make_int2((int32_t)(kk[u] - (int64_t)dd[u] * rows), home0 + j);
+                    sdst[loc] = glob | ((unsigned int)dd[u] << 28);
+                }
+            }
+            __syncwarp();
+            for (unsigned int e = lane; e < total; e += 32) {
+                const unsigned int w = sdst[e];
+                H.peer[w >> 28].inbox[w & 0x0FFFFFFFu] = stage[e];
+            }
+            __syncwarp();
+            if (lane < G) run += cnt;
         }
-        shard_xsync(grid, H, epoch);
-        stamp(5);
-        // S4 + S5: the owner's local sort, positions to the home ranks, segment bounds
+        __syncthreads();
+    };
+    // S4 + S5: the owner's local sort, positions to the home ranks, segment bounds
+    auto local_sort = [&]() {
+        n_in = n_next;
         const int src = shard_sort<WARPS>(grid, s_whist, s_base, s_wsum, n_in, old_n, H, L, me, b, nb);
         shard_bounds<WARPS>(L.kv[src], n_in, own.seg, b, nb);
         old_n = n_in;
         if (rtid == 0) L.ctr[1] = (unsigned int)n_in;
-        shard_xsync(grid, H, epoch);
-        stamp(6);
     };
 
-    if (!H.sorted_valid) sort_step(L.st_a);
+    if (!H.sorted_valid) {  // the order of the states this launch starts from
+        unsigned int cnt = 0;
+        for (int base = part_lo; base < part_hi; base += 32) {
+            const int j = base + lane;
+            count_tile(j < part_hi ? (int)(__ldcg(L.st_a + j) / rows) : -1, cnt);
+        }
+        file_counts(cnt);
+        grid.sync();
+        scan_counts();
+        shard_xsync(grid, H, epoch);
+        scatter_pairs(L.st_a);
+        shard_xsync(grid, H, epoch);
+        local_sort();
+        shard_xsync(grid, H, epoch);
+    }
 
     for (int k = 0; k < H.steps; ++k) {
         kstep = k;
@@ -417,40 +484,71 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
         double loc_sum = 0.0;
         unsigned int loc_cnt = 0;
 
-        // ---------------- phase A: select + environment step of the home agents; records go to the owners of their states
-        for (int base = (rtid & ~31); base < nh; base += rthreads) {
-            const int j = base + lane;
-            if (j < nh) {
-                const uint32_t gid = (uint32_t)(home0 + j);
-                const int s = cur[j];
-                const int o = (int)(s / rows);
-                const int mypos = __ldcg(own.pos + j);
-                const uint32_t valid = H.use_masks ? mdp_mask((uint32_t)s, H.A, H.env_seed) : full;
-                const bool explore = (uint64_t)stream_u32(H.stream_seed, t_sel, gid, 0u) < thresh;
-                const uint32_t bits1 = stream_u32(H.stream_seed, t_sel, gid, 1u);
-                const float* row = H.peer[o].q + (size_t)(s - (int64_t)o * rows) * H.ld;
-                F8 v[LPR];
+        // ---------------- phase A: select + environment step of the home agents; records go to the owners of their states;
+        // the destinations of the next states are counted on the way (first stage of the next step's sort)
+        // (three tiles in flight per warp: state / position of tile t + 2 and the row of tile t + 1 travel while tile t is finished)
+        unsigned int dcnt = 0;
+        {
+            struct Tile { int s, pos; };
+            auto load_sp = [&](int base) {
+                Tile t{0, 0};
+                if (base + lane < part_hi) { t.s = cur[base + lane]; t.pos = __ldcg(own.pos + base + lane); }
+                return t;
+            };
+            auto load_row = [&](int base, const Tile& t, F8* v) {
 #pragma unroll
-                for (int c = 0; c < LPR; ++c) v[c] = ld_row8(row + 8 * c);
-                float mx;
-                uint32_t tie;
-                lane_row_max_tie<LPR>(v, valid, mx, tie);
-                int a = pick_action(H.A, valid, tie, explore, H.empty_all != 0, bits1);
-                if (a < 0) { atomicOr(L.err, kErrEmpty); a = 0; }
-                int32_t s2 = s;
-                float r = 0.0f;
-                bool term = false;
-                mdp_step(s2, a, (uint32_t)H.S, H.A, H.env_seed, H.term_thresh, stream_u32(H.env_stream_seed, t_env, gid, 2u),
-                         stream_u32(H.env_stream_seed, t_env, gid, 3u), r, term);
-                nxt[j] = s2;
-                own.tw[j] = make_uint4((uint32_t)s2, (uint32_t)mypos, __float_as_uint(r), (uint32_t)a | (term ? 0x80u : 0u) | ((uint32_t)o << 8));
-                H.peer[o].rec[mypos] = make_uint2(gid | ((uint32_t)a << 24) | ((!term && s2 == s) ? (1u << 29) : 0u),
-                                                  term ? __float_as_uint(td_target_s(r, 0.0f, H.gamma)) : kPending);
-                float acc = L.ep_ret[j] + r;
-                if (term) { loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
-                L.ep_ret[j] = acc;
+                for (int c = 0; c < LPR; ++c)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[c].v[q] = 0.0f;
+                if (base + lane < part_hi) {
+                    const int o = (int)(t.s / rows);
+                    const float* row = H.peer[o].q + (size_t)(t.s - (int64_t)o * rows) * H.ld;
+#pragma unroll
+                    for (int c = 0; c < LPR; ++c) v[c] = ld_row8(row + 8 * c);
+                }
+            };
+            Tile ta = load_sp(part_lo), tb = load_sp(part_lo + 32);
+            F8 va[LPR], vb[LPR];
+            load_row(part_lo, ta, va);
+            for (int base = part_lo; base < part_hi; base += 32) {
+                const Tile tc = load_sp(base + 64);
+                load_row(base + 32, tb, vb);
+                const int j = base + lane;
+                int dnext = -1;
+                if (j < part_hi) {
+                    const uint32_t gid = (uint32_t)(home0 + j);
+                    const int s = ta.s, mypos = ta.pos;
+                    const int o = (int)(s / rows);
+                    const uint32_t valid = H.use_masks ? mdp_mask((uint32_t)s, H.A, H.env_seed) : full;
+                    const bool explore = (uint64_t)stream_u32(H.stream_seed, t_sel, gid, 0u) < thresh;
+                    const uint32_t bits1 = stream_u32(H.stream_seed, t_sel, gid, 1u);
+                    float mx;
+                    uint32_t tie;
+                    lane_row_max_tie<LPR>(va, valid, mx, tie);
+                    int a = pick_action(H.A, valid, tie, explore, H.empty_all != 0, bits1);
+                    if (a < 0) { atomicOr(L.err, kErrEmpty); a = 0; }
+                    int32_t s2 = s;
+                    float r = 0.0f;
+                    bool term = false;
+                    mdp_step(s2, a, (uint32_t)H.S, H.A, H.env_seed, H.term_thresh, stream_u32(H.env_stream_seed, t_env, gid, 2u),
+                             stream_u32(H.env_stream_seed, t_env, gid, 3u), r, term);
+                    nxt[j] = s2;
+                    dnext = (int)(s2 / rows);
+                    own.tw[j] = make_uint4((uint32_t)s2, (uint32_t)mypos, __float_as_uint(r), (uint32_t)a | (term ? 0x80u : 0u) | ((uint32_t)o << 8));
+                    H.peer[o].rec[mypos] = make_uint2(gid | ((uint32_t)a << 24) | ((!term && s2 == s) ? (1u << 29) : 0u),
+                                                      term ? __float_as_uint(td_target_s(r, 0.0f, H.gamma)) : kPending);
+                    float acc = L.ep_ret[j] + r;
+                    if (term) { loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
+                    L.ep_ret[j] = acc;
+                }
+                count_tile(dnext, dcnt);
+                ta = tb;
+                tb = tc;
+#pragma unroll
+                for (int c = 0; c < LPR; ++c) va[c] = vb[c];
             }
         }
+        file_counts(dcnt);
         {
             for (int d = 16; d > 0; d >>= 1) {
                 loc_sum += __shfl_xor_sync(kFull, loc_sum, d);
@@ -468,8 +566,14 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
         }
         if (rtid == 0) L.ctr[0] = 0u;
         stamp(7);
+        grid.sync();
+        scan_counts();
         shard_xsync(grid, H, epoch);
         stamp(1);
+
+        // ---------------- (sort, stage 3) the pairs of the next order travel to their owners' inboxes
+        scatter_pairs(nxt);
+        stamp(4);
 
         // ---------------- phase T: in-order target pipeline over the home agents (qe_pipe.cuh), rows / records / targets
         // through peer pointers
@@ -510,7 +614,7 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
                 bool fresh = false;
                 uint2 sg = make_uint2(0u, 0u);
                 F8 rowv[LPR];
-                if (cb < nh && (__popc(freeb) >= 8 || (freeb != 0u && (spins & 3u) == 0u))) {
+                if (cb < nh && freeb != 0u) {  // (latency of the peer accesses, not issue slots, bounds this loop: refill at once)
                     const int cc = min(32, nh - cb);
                     const int src = pn + __popc(freeb & ((1u << lane) - 1u));
                     const uint32_t y2 = __shfl_sync(kFull, pd.x, src & 31), pos2 = __shfl_sync(kFull, pd.y, src & 31);
@@ -589,7 +693,11 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
                         reinterpret_cast<float4*>(myrow)[2 * c + 1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
                     }
                     p = sg.x; pe = sg.y;
-                    if (!(p < pe && pe <= (uint32_t)H.n_total)) p = pe = 0u;
+                    if (!(p < pe && pe <= (uint32_t)H.n_total)) {  // nobody stands on s': the untouched row is the answer
+                        p = pe = 0u;
+                        st_relaxed_sys_u32(mytarget, __float_as_uint(td_target_s(r, row_max(), H.gamma)));
+                        busy = false;
+                    }
                 }
                 if (cb >= nh && !__any_sync(kFull, busy)) break;
                 if ((spins & 255u) == 255u) {
@@ -682,8 +790,10 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
         __syncthreads();
         stamp(3);
 
-        // ---------------- phase S: the next step's order
-        sort_step(nxt);
+        // ---------------- (sort, stages 4 and 5) the owner's local sort of its inbox, positions to the home ranks, bounds
+        local_sort();
+        shard_xsync(grid, H, epoch);
+        stamp(6);
     }
     if (H.steps & 1) {
         for (int j = rtid; j < nh; j += rthreads) L.st_a[j] = L.st_b[j];

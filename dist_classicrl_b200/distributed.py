@@ -460,8 +460,7 @@ class ShardedQLearning:
         k = max(1, min(int(steps), 16, self.launch_steps))
         t = np.asarray(list(buf), dtype=np.float64).reshape(16, 8)[:k]
         d = lambda a, b: float(np.mean(t[:, a] - t[:, b]) / 1e3)  # noqa: E731
-        return {"A_work": d(7, 0), "A_barrier": d(1, 7), "T": d(2, 1), "C": d(3, 2), "sort_counts": d(4, 3), "sort_scatter": d(5, 4),
-                "sort_local": d(6, 5), "step": d(6, 0)}
+        return {"A_work": d(7, 0), "A_barrier": d(1, 7), "sort_scatter": d(4, 1), "T": d(2, 4), "C": d(3, 2), "sort_local": d(6, 3), "step": d(6, 0)}
 
     def sync(self) -> None:
         """Wait for this rank's kernels and raise deferred device errors."""
