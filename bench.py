@@ -5,17 +5,21 @@
 
 One "step" = one vector step of all agents (N_agents agent-steps).  Metric: agent-steps/s (BASELINE.json).
 Workload at --gpus 1: BASELINE config 3 -- hash MDP, 1 000 000 states x 16 actions, 2^20 agents, masked actions,
-eps 0.1, lr 0.1, gamma 0.99, uniform[0,1) initial table, on-device counter stream.  With --gpus N > 1 (torchrun,
-one rank per GPU) every GPU runs that workload on its own replica of the table and the replicas are merged by a
-Q-delta all-reduce every 8 vector steps (config 5; weak scaling); a bounded run of the state-range-sharded table of
-config 4 (100 M states x 8 actions, 2^22 agents in total) is reported beside it under `sharded_c4`.
+eps 0.1, lr 0.1, gamma 0.99, uniform[0,1) initial table, on-device counter stream (`--workload c2` / `c4`: configs 2 and
+4 on one GPU).  With --gpus N > 1 (torchrun, one rank per GPU) every GPU runs that workload on its own replica of the
+table and the replicas are merged by a Q-delta all-reduce every 8 vector steps (config 5; weak scaling); the
+state-range-sharded table of config 4 (100 M states x 8 actions, 2^22 agents in total, peer memory over NVLink) is
+reported beside it under `sharded_c4`, and `multi_gpu_parity` says whether the sharded and the replicated mode reproduced
+the C oracle on a small case in this very run.
 
-Prints ONE JSON line (see the contract in the task description): `value` = device-resident throughput
-(CUDA events around the K timed steps, 8 vector steps per fused launch; the working set is larger than L2), `e2e` = the same metric
-through the reference-shaped public API (`SingleThreadQLearning.run_steps`) with the step's pre-drawn uniforms
-copied host->device from pinned memory and the step's results copied back, `roofline` (HBM), `cpu_baseline`
-(C port of the reference loop on the host cores), `clocks`, `gpu_launches`.
-`--impl reference` times the CPU restatement of the reference (oracle/c) on the same workload.
+Prints ONE JSON line (see the contract in the task description): `value` = device-resident throughput (CUDA events around
+the K timed steps that follow W warm-up steps, 8 vector steps per fused launch), `value_long` = the same over the first
+512 vector steps of a fresh run (the workload drifts: agents herd as the table is learned), `e2e` = the same metric
+through the reference-shaped public API (`SingleThreadQLearning.run_steps`) with the step's pre-drawn uniforms copied
+host->device from pinned memory and the step's results copied back, `roofline` (HBM; `gather_peak` = what dependency-free
+random row gathers reach on this table), `cpu_baseline` (the unmodified reference from baseline/_ref: single-thread and
+multiprocessing trainers, MPI recorded as not runnable; C and NumPy ports beside it), `clocks`, `gpu_launches`.
+`--impl reference` times the unmodified reference (baseline/_ref) on the host cores, on a bounded sample of the workload.
 """
 
 from __future__ import annotations
@@ -221,6 +225,119 @@ def python_port_rate(workload: str, agents: int, steps: int):
 
 
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+FORM_NAMES = {0: "writer lists", 1: "per-step sort", 3: "target pipeline"}
+FORM_KERNELS = {0: "fused_kernel", 1: "fused_sorted_kernel", 3: "fused_pipe_kernel"}
+
+
+class TwinEnv:
+    """gym-style ``reset()`` / ``step(actions)`` on top of the oracle's NumPy environment (the reference's trainers need
+    gymnasium for their own environments, which is not installed): one row of the uniform stream per step."""
+
+    def __init__(self, workload: str, agents: int, agent0: int = 0):
+        from oracle.envs import HashMDPVec, TicTacToeVec
+
+        s, a, _n, _ = WORKLOADS[workload]
+        self.inner = TicTacToeVec(agents) if workload == "c2" else HashMDPVec(agents, s, a, seed=ENV_SEED, p_term=P_TERM)
+        self.slots = 5 if workload == "c2" else 4
+        self.t = 0
+        self.num_envs = agents
+        self.agent0 = agent0
+
+    def reset(self, seed=None):
+        from oracle import rng as orng
+        from oracle.envs import T_INIT
+
+        return self.inner.reset(orng.draw_uniforms(STREAM_SEED, T_INIT, 1, self.num_envs, self.slots, agent0=self.agent0)[0])
+
+    def step(self, actions):
+        from oracle import rng as orng
+
+        u = orng.draw_uniforms(STREAM_SEED, self.t, 1, self.num_envs, self.slots, agent0=self.agent0)[0]
+        self.t += 1
+        return self.inner.step(actions, u)
+
+
+def _import_reference():
+    if not os.path.isdir(os.path.join(REF_DIR, "dist_classicrl")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        from dist_classicrl.algorithms.base_algorithms.q_learning_optimal import OptimalQLearningBase as RefQL
+        from dist_classicrl.algorithms.runtime.base_runtime import BaseRuntime as RefRuntime
+        from dist_classicrl.algorithms.runtime.parallel_runtime import ParallelQLearning as RefParallel
+        from dist_classicrl.schedules.constant_schedule import ConstantSchedule as RefConstant
+    except Exception:  # noqa: BLE001
+        return None
+    return RefQL, RefRuntime, RefParallel, RefConstant
+
+
+def reference_parallel_rates(workload: str, agents_per_env: int, steps_per_proc: int, procs: list[int]) -> dict:
+    """agent-steps/s of the UNMODIFIED reference's multiprocessing trainer (``ParallelQLearning.run_steps``, PRT:80-165:
+    one process per environment, the table in shared memory, ONE lock around ``choose_actions`` and ``learn``) with P
+    environments of ``agents_per_env`` agents each, the reference's own throughput formula (agent-steps of all processes /
+    wall time around ``run_steps``, process start-up included, TPB:222-249)."""
+    ref = _import_reference()
+    if ref is None:
+        return {}
+    RefQL, _RefRuntime, RefParallel, RefConstant = ref
+    s, a, _n, _ = WORKLOADS[workload]
+    out = {}
+    for p in procs:
+        algo = RefQL(s, a, GAMMA, seed=STREAM_SEED)
+        if workload != "c2":
+            algo.q_table = np.random.default_rng(TABLE_SEED).random((s, a))
+        rt = RefParallel(algo, RefConstant(LR), RefConstant(EPS))
+        envs = [TwinEnv(workload, agents_per_env, agent0=k * agents_per_env) for k in range(p)]
+        try:
+            rt.init_training()
+            t = time.perf_counter()
+            rt.run_steps(steps_per_proc * p, envs, None)
+            dt = time.perf_counter() - t
+            out[str(p)] = {"value": p * steps_per_proc * agents_per_env / dt, "seconds": dt}
+        except Exception as exc:  # noqa: BLE001
+            out[str(p)] = {"error": repr(exc)}
+        finally:
+            try:
+                rt.close_training()
+            except Exception:  # noqa: BLE001
+                pass
+    return out
+
+
+def cpu_baselines(workload: str, ref_steps: int = 4, quick: bool = False) -> dict:
+    """Everything the GPU numbers are printed next to, timed on THIS host (no CUDA in this process): the unmodified
+    reference single-threaded and through its multiprocessing trainer, its MPI trainer recorded as not runnable, and the
+    C / NumPy ports of the same loop."""
+    s, a, n, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    out = {"cores_on_host": cores}
+    ref_agents = min(n, 1 << 12)
+    ref = reference_rate(workload, ref_agents, ref_steps)
+    if ref is not None:
+        out["single_thread"] = {"value": ref[0], "cores": 1, "sample": f"{ref_steps} vector steps x {ref_agents} agents ({ref[1]:.1f} s); {ref[2]}"}
+        procs = sorted({p for p in (1, 2, 4, 8, cores) if p <= cores})
+        per_env = min(n, 1 << 11)
+        spp = (50 if quick else 200) if workload == "c2" else (2 if quick else 8)
+        par = reference_parallel_rates(workload, per_env, spp, procs)
+        out["multiprocessing"] = {"trainer": "unmodified reference ParallelQLearning.run_steps (one process per environment, shared-memory table, one lock around choose_actions and learn)",
+                                  "agents_per_env": per_env, "vector_steps_per_process": spp, "by_processes": par,
+                                  "formula": "agent-steps of all processes / wall time around run_steps (process start-up included, as the reference's throughput_benchmark.py does)"}
+        good = [(v["value"], int(p)) for p, v in par.items() if "value" in v]
+        if good:
+            best = max(good)
+            out["multiprocessing"]["best"] = {"value": best[0], "processes": best[1]}
+    out["mpi"] = {"value": None, "status": "not runnable here: neither mpi4py nor an MPI launcher is installed (image and wheelhouse)",
+                  "published_i7_11700K": {"8_ranks_128_agents": 76098, "2_ranks_128_agents": 22596, "source": "BASELINE.md (benchmark_results/distributed_128_agents_*_processes.json)"}}
+    cpu_agents = n if workload == "c2" else 1 << 20
+    cpu_steps = 2000 if workload == "c2" else (4 if quick else 12)
+    rate, dt = cpu_port_rate(workload if workload != "c4" else "c3", cpu_agents, cpu_steps)
+    out["c_port"] = {"value": rate, "cores": cores, "sample": f"{cpu_steps} vector steps x {cpu_agents} agents, C port of the reference loop: OpenMP select + env step, sequential learn ({dt:.1f} s)"
+                     + (" [config 3's table: config 4's 100M x 8 fp32 table is 3.2 GB per copy]" if workload == "c4" else "")}
+    py_agents, py_steps = (n, 50) if workload == "c2" else (1 << 13, 2 if quick else 4)
+    out["python_port"] = {"value": python_port_rate(workload if workload != "c4" else "c3", py_agents, py_steps), "cores": 1,
+                          "sample": f"{py_steps} vector steps x {py_agents} agents, NumPy/Python restatement"}
+    return out
 
 
 def reference_rate(workload: str, agents: int, steps: int, warm: int = 1):
@@ -229,19 +346,10 @@ def reference_rate(workload: str, agents: int, steps: int, warm: int = 1):
     ``BaseRuntime.run_single_step`` -- the loop body of ``SingleThreadQLearning.run_steps`` (STR:63-64), which itself
     cannot be imported without gymnasium -- on the NumPy twin of the workload's environment.  Single-threaded, like the
     reference.  Returns (rate, seconds, description) or None if the reference is not installed."""
-    if not os.path.isdir(os.path.join(REF_DIR, "dist_classicrl")):
+    ref = _import_reference()
+    if ref is None:
         return None
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
-    try:
-        from dist_classicrl.algorithms.base_algorithms.q_learning_optimal import OptimalQLearningBase as RefQL
-        from dist_classicrl.algorithms.runtime.base_runtime import BaseRuntime as RefRuntime
-        from dist_classicrl.schedules.constant_schedule import ConstantSchedule as RefConstant
-    except Exception:  # noqa: BLE001
-        return None
-    from oracle import rng as orng
-    from oracle.envs import T_INIT, HashMDPVec, TicTacToeVec
-
+    RefQL, RefRuntime, _RefParallel, RefConstant = ref
     s, a, _n, _ = WORKLOADS[workload]
 
     class Loop(RefRuntime):  # the ABC's three abstract hooks; everything that runs is the reference's
@@ -254,26 +362,11 @@ def reference_rate(workload: str, agents: int, steps: int, warm: int = 1):
         def close_training(self):
             return None
 
-    class Env:  # gym-style step(actions) on top of the oracle environment, one row of the uniform stream per step
-        def __init__(self):
-            self.inner = TicTacToeVec(agents) if workload == "c2" else HashMDPVec(agents, s, a, seed=ENV_SEED, p_term=P_TERM)
-            self.slots = 5 if workload == "c2" else 4
-            self.t = 0
-            self.num_envs = agents
-
-        def reset(self):
-            return self.inner.reset(orng.draw_uniforms(STREAM_SEED, T_INIT, 1, agents, self.slots)[0])
-
-        def step(self, actions):
-            u = orng.draw_uniforms(STREAM_SEED, self.t, 1, agents, self.slots)[0]
-            self.t += 1
-            return self.inner.step(actions, u)
-
     algo = RefQL(s, a, GAMMA, seed=STREAM_SEED)
     if workload != "c2":
         algo.q_table = np.random.default_rng(TABLE_SEED).random((s, a))
     rt = Loop(algo, RefConstant(LR), RefConstant(EPS))
-    env = Env()
+    env = TwinEnv(workload, agents)
     states, _ = env.reset()
     rewards = np.zeros(agents, dtype=np.float32)
     history: list = []
@@ -288,50 +381,136 @@ def reference_rate(workload: str, agents: int, steps: int, warm: int = 1):
 
 
 def run_reference(args) -> dict:
-    """`--impl reference`: the CPU restatement of the reference's path, all host threads, bounded sample."""
+    """`--impl reference`: the unmodified reference (baseline/_ref) on this host's cores, bounded sample of the workload:
+    its single-thread trainer loop and its multiprocessing trainer with 1, 2, 4, 8, ... processes; the line's value is the
+    best of them (the reference "with all the host threads it can use")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         sys.exit(0)
     workload = args.workload or "c3"
     s, a, n, desc = WORKLOADS[workload]
-    # bounded sample: the reference loop is sequential in the agents, so per-agent-step cost does not depend on
-    # the batch size; cap the agents so that warm-up + K steps stay within a few minutes
-    steps = max(1, args.steps)
-    # the reference itself (single-threaded Python: ~25 us per agent-step whatever the batch size) on a bounded sample
-    ref_agents = min(n, 1 << 12)
-    ref = reference_rate(workload, ref_agents, steps, warm=min(args.warmup, 2) or 1)
-    agents = min(n, 1 << 20)
-    port_rate, port_dt = cpu_port_rate(workload, agents, min(steps, 12), warm=1)
+    steps = max(1, min(args.steps, 8))
+    base = cpu_baselines(workload, ref_steps=steps, quick=False)
     cores = os.cpu_count() or 1
-    port_sample = f"{min(steps, 12)} vector steps x {agents} agents of the same workload (C port of the reference loop, OpenMP select+env, sequential learn)"
-    if ref is not None:
-        rate, dt, how = ref
-        return {
-            "impl": "reference", "metric": "agent-steps/s", "value": rate, "unit": "agent-steps/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{workload}: {desc}", "states": s, "actions": a, "agents_per_gpu": n, "agents": n * args.gpus,
-                       "sample_agents": ref_agents, "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM,
-                       "ms_per_full_step_scaled": dt / steps * 1e3 * (n / ref_agents),
-                       "note": "a step of this arm is one vector step of the SAMPLE (sample_agents agents); the reference's cost per agent-step does not depend on the batch size"},
-            "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": 1, "kind": "reference",
-                             "sample": f"{steps} vector steps x {ref_agents} agents of the same workload; {how}",
-                             "c_port_value": port_rate, "c_port_cores": cores, "c_port_sample": port_sample},
-            "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }
-    rate, dt, sample = port_rate, port_dt, port_sample
-    steps = min(steps, 12)
+    cands = []
+    if "single_thread" in base:
+        cands.append((base["single_thread"]["value"], 1, "single-thread trainer loop: " + base["single_thread"]["sample"]))
+    if "multiprocessing" in base and "best" in base["multiprocessing"]:
+        mpb = base["multiprocessing"]
+        cands.append((mpb["best"]["value"], mpb["best"]["processes"],
+                      f"multiprocessing trainer, {mpb['best']['processes']} processes x {mpb['agents_per_env']} agents x {mpb['vector_steps_per_process']} vector steps each; {mpb['trainer']}"))
+    kind = "reference"
+    if not cands:  # baseline/_ref is missing: the C port stands in
+        cands.append((base["c_port"]["value"], cores, base["c_port"]["sample"]))
+        kind = "port"
+    rate, used, sample = max(cands)
+    ref_agents = min(n, 1 << 12)
     return {
         "impl": "reference", "metric": "agent-steps/s", "value": rate, "unit": "agent-steps/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload}: {desc}", "states": s, "actions": a, "agents_per_gpu": n, "agents": n * args.gpus, "sample_agents": agents,
-                   "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM},
-        "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "steps": steps, "warmup": args.warmup, "ms_per_step": ref_agents / rate * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if kind == "reference" else "f32", "data": "synthetic",
+        "config": {"workload": f"{workload}: {desc}", "states": s, "actions": a, "agents_per_gpu": n, "agents": n * args.gpus,
+                   "sample_agents": ref_agents, "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM,
+                   "note": "a step of this arm is one vector step of the SAMPLE (sample_agents agents); the reference's cost per agent-step "
+                           "does not depend on the batch size (a per-agent Python loop), so agent-steps/s carries over to the full batch"},
+        "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": used, "kind": kind, "sample": sample, **{k: v for k, v in base.items()}},
         "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+
+
+def cpu_baselines_subprocess(workload: str) -> dict | None:
+    """The CPU arms in a FRESH interpreter (the reference's multiprocessing trainer forks: not from a process that holds a
+    CUDA context)."""
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "_cpu", "--workload", workload], capture_output=True, text=True,
+                             timeout=900, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+        for line in reversed(res.stdout.splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+    except Exception:  # noqa: BLE001
+        return None
+    return None
+
+
+def multi_gpu_parity(tp, local: int, torch) -> dict:
+    """Sharded and replicated modes on small cases, this very set of GPUs, against the C oracle (rank 0 compares):
+    sharded -- table, agent states and running returns bit for bit; replicated -- states bit for bit and the merged table
+    against the NumPy restatement of the delta rule (exact for two ranks, 1e-6 relative beyond: the order in which the
+    all-reduce adds more than two fp32 terms is NCCL's)."""
+    from dist_classicrl_b200 import distributed as D
+    from dist_classicrl_b200.algorithms.base_algorithms.q_learning_optimal import OptimalQLearningBase
+    from dist_classicrl_b200.algorithms.runtime import SingleThreadQLearning
+    from dist_classicrl_b200.environments import HashMDPVecEnv
+    from dist_classicrl_b200.schedules import ConstantSchedule
+    from oracle import c_oracle as co
+    from oracle import rng as orng
+    from oracle.envs import T_INIT
+
+    tt = int(math.ceil(P_TERM * 2.0**32))
+    out = {}
+
+    def rnd_table(S, A, seed):
+        x = (np.arange(S * A, dtype=np.uint64) ^ np.uint64((seed * 0x9E3779B9) & 0xFFFFFFFF)) & np.uint64(0xFFFFFFFF)
+        x ^= x >> np.uint64(16)
+        x = (x * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+        x ^= x >> np.uint64(13)
+        x = (x * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+        x ^= x >> np.uint64(16)
+        return ((x >> np.uint64(8)).astype(np.float32) * np.float32(2.0**-24)).reshape(S, A)
+
+    # sharded
+    S, A, N, steps, seed, env_seed = 300_000, 16, 100_000, 6, 7, 3
+    sh = D.ShardedQLearning(S, A, GAMMA, N, tp, env_seed=env_seed, p_term=P_TERM, seed=seed, device=local)
+    sh.fill_random(TABLE_SEED)
+    sh.reset()
+    sh.run_steps(steps, ConstantSchedule(EPS), ConstantSchedule(LR))
+    table = sh.gather_table()
+    states, rets = sh.gather_agents()
+    sh.close()
+    if tp.rank == 0:
+        st_o, mk_o = co.mdp_reset(orng.draw_uniforms(seed, T_INIT, 1, N, 4)[0], S, A, env_seed)
+        q_o = rnd_table(S, A, TABLE_SEED)
+        rew = np.zeros(N, dtype=np.float32)
+        res = co.run(co.ENV_MDP, q_o, None, st_o, mk_o, num_states=S, env_seed=env_seed, term_thresh=tt, uniforms=None, slots=4, stream_seed=seed,
+                     steps=steps, eps_thresh=np.full(steps, orng.explore_threshold(EPS), dtype=np.uint64), lr=np.full(steps, LR, np.float32), gamma=GAMMA,
+                     empty_all=A > 10, agent_rewards=rew)
+        ok = res["rc"] == 0 and np.array_equal(states, st_o) and np.array_equal(table, q_o) and np.array_equal(rets, rew)
+        out["sharded"] = {"result": "pass" if ok else "FAIL", "case": f"{S} states x {A} actions, {N} agents, {steps} vector steps, {tp.world_size} GPUs: table, states, returns bit-exact vs the C oracle"}
+    # replicated: one merge period
+    S, A, n_local, k, seed, env_seed = 3000, 8, 2048, 4, 11, 2
+    algo = OptimalQLearningBase(S, A, GAMMA, seed=seed, device=local)
+    algo.fill_random(TABLE_SEED)
+    env = HashMDPVecEnv(n_local, S, A, env_seed=env_seed, p_term=P_TERM, seed=seed, device=local, output="torch")
+    env.agent0 = tp.rank * n_local
+    env.attach(algo)
+    rt = SingleThreadQLearning(algo, ConstantSchedule(LR), ConstantSchedule(EPS))
+    rt.history_mode = "summary"
+    rep = D.ReplicatedQLearning(rt, tp, sync_every=k)
+    rep.run_steps(k, env)
+    mine = torch.stack([env.states.to(torch.int32)]).reshape(1, -1).contiguous()
+    all_states = tp.all_gather_rows(mine).cpu().numpy()
+    merged = np.array(algo.q_table, copy=True)
+    if tp.rank == 0:
+        base = rnd_table(S, A, TABLE_SEED)
+        acc = np.zeros_like(base, dtype=np.float64)
+        good = True
+        for r in range(tp.world_size):
+            st_r = co.mdp_reset(orng.draw_uniforms(seed, T_INIT, 1, n_local, 4, agent0=r * n_local)[0], S, A, env_seed)
+            q = base.copy()
+            res = co.run(co.ENV_MDP, q, None, st_r[0], st_r[1], num_states=S, env_seed=env_seed, term_thresh=tt, uniforms=None, slots=4, stream_seed=seed,
+                         t0=0, agent0=r * n_local, steps=k, eps_thresh=np.full(k, orng.explore_threshold(EPS), dtype=np.uint64), lr=np.full(k, LR, np.float32),
+                         gamma=GAMMA, empty_all=A > 10)
+            good = good and res["rc"] == 0 and np.array_equal(all_states[r], st_r[0])
+            acc += (q - base).astype(np.float64)
+        want = base.astype(np.float64) + acc
+        err = float(np.max(np.abs(merged.astype(np.float64) - want) / np.maximum(1.0, np.abs(want))))
+        good = good and err <= 1e-6
+        out["replicated"] = {"result": "pass" if good else "FAIL", "max_rel_err_table": err,
+                             "case": f"{S} states x {A} actions, {n_local} agents per GPU, one merge after {k} steps, {tp.world_size} GPUs: states bit-exact, merged table within 1e-6 of base + sum of the oracle's deltas"}
+        out["result"] = "pass" if all(v.get("result") == "pass" for v in out.values() if isinstance(v, dict)) else "FAIL"
+    del algo, env, rep, rt
+    return out
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -368,9 +547,7 @@ def run_ours(args) -> dict | None:
     workload = args.workload or "c3"
     s, a, n, desc = WORKLOADS[workload]
     lib = capi.lib()
-    # the engine times its first launches of both forms of the TD update before it settles on one: give it five
-    # launches of warm-up at least
-    K, W = args.steps, max(3, args.warmup, 5 * SYNC_EVERY)
+    K, W = args.steps, max(3, args.warmup)  # (at least three warm-up steps; the first launch also pays for module loading)
     # 128 TicTacToe agents take ~11 us per vector step: only long launches amortise the ~40 us a launch costs
     per_launch = 256 if (workload == "c2" and world == 1) else SYNC_EVERY
     stream = torch.cuda.current_stream()
@@ -454,26 +631,8 @@ def run_ours(args) -> dict | None:
         b.synchronize()
         return a.elapsed_time(b)
 
-    def calibrate(chunk_list) -> dict:
-        """The exact TD update has two forms with identical results (writer lists / per-step sort); which one is faster
-        depends on how far the agents have herded.  The engine's own selection times its launches as they happen and
-        probes the other form every 12 launches -- inside a 5-launch window that is noise -- so the bench decides the
-        same way (time each form at the current training progress, keep the faster) but once, during warm-up, and pins
-        the result for the window.  Consumes 4 chunks of `chunk_list` (one cold + one timed launch per form)."""
-        ms = {}
-        for form in (0, 1):
-            capi.check(lib.qe_set_fused_form(algo.handle, form))
-            launch(chunk_list.pop(0))
-            k = chunk_list.pop(0)
-            ms[form] = timed_launch(k) / k
-        best = 0 if ms[0] <= ms[1] else 1
-        capi.check(lib.qe_set_fused_form(algo.handle, best))
-        return {"writer_lists_ms_per_step": ms[0], "per_step_sort_ms_per_step": ms[1], "picked": ["writer lists", "per-step sort"][best]}
-
-    calibration = None
+    calibration = None  # (round 1 timed two forms of the exact update against each other here; the target pipeline replaced both)
     warm = chunks(W)
-    if rep is None and workload != "c2" and "QE_SORTED" not in os.environ and len(warm) >= 5:
-        calibration = calibrate(warm)
     for k in warm:
         launch(k)
         if rep is not None:
@@ -493,15 +652,8 @@ def run_ours(args) -> dict | None:
     kernel_events = []
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_begin.record(stream)
-    # long windows: the workload drifts, so the pinned form is looked at again every 12 launches -- the other form, then
-    # the current one, in two adjacent launches of the window (they are ordinary steps of the run), like the engine's
-    # own selection does
-    cur_form = int(lib.qe_fused_form(algo.handle))
     reprobes = []
     for j, k in enumerate(chunks(K)):
-        probing = calibration is not None and j >= 12 and (j % 12) in (0, 1)
-        if probing:
-            capi.check(lib.qe_set_fused_form(algo.handle, cur_form ^ 1 if j % 12 == 0 else cur_form))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         launch(k)
@@ -509,14 +661,6 @@ def run_ours(args) -> dict | None:
         kernel_events.append((k, e0, e1))
         if rep is not None:
             rep.sync()
-        if probing and j % 12 == 1:
-            e1.synchronize()
-            (ka, a0, a1), (kb, b0, b1) = kernel_events[-2], kernel_events[-1]
-            other, mine = a0.elapsed_time(a1) / ka, b0.elapsed_time(b1) / kb
-            if other < mine:
-                cur_form ^= 1
-            capi.check(lib.qe_set_fused_form(algo.handle, cur_form))
-            reprobes.append({"launch": j, "other_ms_per_step": other, "current_ms_per_step": mine, "now": ["writer lists", "per-step sort"][cur_form]})
     e_end.record(stream)
     sync_all()
     capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
@@ -535,34 +679,51 @@ def run_ours(args) -> dict | None:
     value = world * n * K / (total_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
     grid_blocks = int(lib.qe_fused_grid_blocks(algo.handle))
-    fused_form = ["writer lists", "per-step sort"][int(lib.qe_fused_form(algo.handle))]
-    buf = (C.c_uint64 * 33)()
-    m = lib.qe_fused_phase_ns(algo.handle, buf, 33)
+    form_id = int(lib.qe_fused_form(algo.handle))
+    fused_form = FORM_NAMES.get(form_id, str(form_id))
+    buf = (C.c_uint64 * 48)()
+    m = lib.qe_fused_phase_ns(algo.handle, buf, 48)
     phases = None
     if m >= 4:
         ks = (m - 1) // 3
-        phases = {name: sum(buf[1 + ph + 3 * j] - buf[ph + 3 * j] for j in range(ks)) / ks / 1e3
-                  for ph, name in enumerate(("select_step_register_us", "td_first_pass_us", "td_deferred_us"))}
+        names = ("select_env_step_us", "target_pipeline_us", "commit_and_sort_us") if form_id == 3 else ("select_step_register_us", "td_first_pass_us", "td_deferred_us")
+        phases = {name: sum(buf[1 + ph + 3 * j] - buf[ph + 3 * j] for j in range(ks)) / ks / 1e3 for ph, name in enumerate(names)}
+        if form_id == 3:
+            phases["commit_us"] = sum(buf[32 + j] - buf[2 + 3 * j] for j in range(ks)) / ks / 1e3
+            phases["sort_us"] = sum(buf[3 + 3 * j] - buf[32 + j] for j in range(ks)) / ks / 1e3
+    gather_peak = float(lib.qe_debug_gather_gbs(algo.handle)) if rank == 0 else None
     # The workload drifts: a greedy policy on a deterministic MDP herds agents onto the same rows, and the rows get more
-    # crowded as the table is learned.  Report the same measurement once more after 256 vector steps.
+    # crowded as the table is learned.  value_long: a fresh run, vector steps 0..512, one number; late_training: its window
+    # of steps 256..288.
     late = None
+    value_long = None
     if world == 1 and workload != "c2" and not args.no_late:
-        while t_next[0] < 256 - 4 * SYNC_EVERY:
-            launch(SYNC_EVERY)
-        late_cal = calibrate([SYNC_EVERY] * 4) if calibration is not None else None
-        while t_next[0] < 256:
-            launch(SYNC_EVERY)
-        capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record(stream)
-        for _ in range(4):
-            launch(SYNC_EVERY)
-        l1.record(stream)
+        del algo, env
+        algo, env = make()
+        ep_ret = torch.zeros(n, dtype=torch.float32, device=dev)
+        ag = env.agents_struct(ep_ret)
+        t_next[0] = 0
+        launch(SYNC_EVERY)  # (module / scratch already warm; these steps are part of the horizon but not of the clock)
+        horizon = 512
+        marks = [torch.cuda.Event(enable_timing=True)]
+        marks[0].record(stream)
+        while t_next[0] < horizon:
+            for _ in range(4):
+                launch(SYNC_EVERY)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            marks.append(ev)
         torch.cuda.synchronize()
         capi.check(lib.qe_sync(algo.handle, C.c_void_p(stream.cuda_stream)))
-        late_ms = l0.elapsed_time(l1) / (4 * SYNC_EVERY)
-        late = {"td_update_form": ["writer lists", "per-step sort"][int(lib.qe_fused_form(algo.handle))], "after_vector_steps": 256, "steps": 4 * SYNC_EVERY, "ms_per_step": late_ms, "value": n / (late_ms * 1e-3), "unit": "agent-steps/s",
-                "form_calibration": late_cal}
+        seg_ms = [marks[j].elapsed_time(marks[j + 1]) / 32 for j in range(len(marks) - 1)]  # ms per vector step, 32-step windows from step 8
+        long_ms = marks[0].elapsed_time(marks[-1])
+        long_steps = 32 * (len(marks) - 1)
+        value_long = {"value": n * long_steps / (long_ms * 1e-3), "unit": "agent-steps/s", "vector_steps": f"8..{8 + long_steps} of a fresh run",
+                      "ms_per_step": long_ms / long_steps, "roofline_frac": n * alg_bytes(a) * long_steps / (long_ms * 1e-3) / 1e9 / measured_peak()[0],
+                      "ms_per_step_by_32_step_window": [round(x, 4) for x in seg_ms]}
+        jl = min(len(seg_ms) - 1, (256 - 8) // 32 + 1)
+        late = {"td_update_form": FORM_NAMES.get(int(lib.qe_fused_form(algo.handle)), "?"), "after_vector_steps": 8 + 32 * jl, "steps": 32, "ms_per_step": seg_ms[jl],
+                "value": n / (seg_ms[jl] * 1e-3), "unit": "agent-steps/s", "roofline_frac": n * alg_bytes(a) / (seg_ms[jl] * 1e-3) / 1e9 / measured_peak()[0]}
     episodes = int(sum_over_ranks(float(ep_cnt.item())))
     del algo, env, rep, rt0
 
@@ -629,29 +790,71 @@ def run_ours(args) -> dict | None:
            "run_steps(1, env, state_dict): the step's pre-drawn uniforms (PredrawnUniforms, pinned host memory) and the state dict's running returns go host->device, the returns and the episode statistics come back, every step"}
     del algo, env, runner, rt
 
-    # ---------------- sharded 100M-state table (config 4), bounded
+    # ---------------- sharded 100M-state table (config 4): peer memory over NVLink, one persistent kernel per GPU
     sharded = None
+    parity = None
     if tp is not None and not args.no_sharded:
         s4, a4, n4, desc4 = WORKLOADS["c4"]
         sh = D.ShardedQLearning(s4, a4, GAMMA, n4, tp, env_seed=ENV_SEED, p_term=P_TERM, seed=STREAM_SEED, device=local)
         sh.fill_random(TABLE_SEED)
         sh.reset()
         eps_s, lr_s = ConstantSchedule(EPS), ConstantSchedule(LR)
-        sh.run_steps(3, eps_s, lr_s)
+        sh.run_steps(8, eps_s, lr_s)
+        sh.sync()
         sync_all()
-        r0 = sh.rounds_total
-        ks = min(K, 10)
+        ks = 16
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0.record(stream)
         sh.run_steps(ks, eps_s, lr_s)
         b1.record(stream)
+        sh.sync()
         sync_all()
         ms = max_over_ranks(b0.elapsed_time(b1))
-        sharded = {"workload": f"c4: {desc4}", "value": n4 * ks / (ms * 1e-3), "unit": "agent-steps/s", "scaling": "strong", "steps": ks,
-                   "ms_per_step": ms / ks, "fixed_point_rounds_per_step": (sh.rounds_total - r0) / ks,
-                   "states": s4, "actions": a4, "agents": n4,
-                   "exchange": "NCCL all-to-all: bootstrap requests + answers per round, agent migration per step"}
+        ph = sh.phase_us()
+        cs = sh.table_checksum()
+        steps_done = 8 + ks
+        sh.close()
         del sh
+        # the same number of steps of the same job on ONE GPU (rank 0 alone, same engine with a world of one): equal tables?
+        cs1 = None
+        ms1 = None
+        if rank == 0:
+            class _Solo(D.Transport):
+                rank, world_size = 0, 1
+
+                def all_reduce_sum_(self, t):
+                    return t
+
+                def all_gather_rows(self, t):
+                    return t
+
+                def barrier(self):
+                    pass
+
+            solo = D.ShardedQLearning(s4, a4, GAMMA, n4, _Solo(), env_seed=ENV_SEED, p_term=P_TERM, seed=STREAM_SEED, device=local)
+            solo.fill_random(TABLE_SEED)
+            solo.reset()
+            solo.run_steps(8, eps_s, lr_s)
+            solo.sync()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            solo.run_steps(ks, eps_s, lr_s)
+            c1.record(stream)
+            solo.sync()
+            ms1 = c0.elapsed_time(c1)
+            cs1 = solo.table_checksum()
+            solo.close()
+            del solo
+        sync_all()
+        sharded = {"workload": f"c4: {desc4}", "value": n4 * ks / (ms * 1e-3), "unit": "agent-steps/s", "scaling": "strong", "steps": ks,
+                   "ms_per_step": ms / ks, "states": s4, "actions": a4, "agents": n4, "phase_us_per_step_rank0": ph,
+                   "table_checksum": f"{cs:016x}", "table_checksum_single_gpu": None if cs1 is None else f"{cs1:016x}",
+                   "equals_single_gpu_table": None if cs1 is None else bool(cs == cs1), "vector_steps_compared": steps_done,
+                   "single_gpu_same_engine": None if ms1 is None else {"value": n4 * ks / (ms1 * 1e-3), "ms_per_step": ms1 / ks},
+                   "exchange": "no collective on the data path: rows, writer records and targets are peer loads / stores over NVLink (slabs in "
+                               "torch symmetric memory), the per-step order is a distributed stable sort, 3 flag barriers in peer memory per step"}
+        # ---------------- does the multi-GPU path compute the right thing HERE?  Small cases against the C oracle on rank 0.
+        parity = multi_gpu_parity(tp, local, torch)
 
     if rank != 0:
         return None
@@ -661,52 +864,52 @@ def run_ours(args) -> dict | None:
     per_launch_ms = kernel_ms / len(kernel_events)
     steps_per_launch = K / len(kernel_events)
     achieved = n * steps_per_launch * balg / (per_launch_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic of the dominant kernel: from the committed ncu capture of this command (never measured under the bench)
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(workload + ("_sorted" if fused_form == "per-step sort" else ""))
+            tj = json.load(open(tpath))
+            ent = tj.get(f"{workload}_form{form_id}")
+            if isinstance(ent, dict):
+                traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:  # noqa: BLE001
             traffic = None
-    kname = ("fused_sorted_kernel" if fused_form == "per-step sort" else "fused_kernel") + ("<MDP,2>" if workload != "c2" else "<TTT,2>")
+    kname = FORM_KERNELS.get(form_id, "fused_kernel") + ("<TTT,2>" if workload == "c2" else ("<MDP,1>" if a <= 8 else "<MDP,2>"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_agent_step": balg,
+                "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_agent_step": balg,
                 "algorithmic_bytes_per_launch": n * steps_per_launch * balg, "avg_launch_ms": per_launch_ms,
-                "steps_per_launch": steps_per_launch, "phase_us_per_step": phases}
+                "steps_per_launch": steps_per_launch, "phase_us_per_step": phases,
+                "gather_peak": {"value": gather_peak, "unit": "GB/s", "what": "dependency-free random whole-row gathers over this table (qe_debug_gather_gbs): "
+                                "the ceiling of the engine's dominant access pattern, to be read beside the copy peak"}}
     cpu_baseline = None
     if world == 1:
-        cpu_agents = n if workload == "c2" else 1 << 20
-        cpu_steps = 2000 if workload == "c2" else 12
-        cpu_rate, cpu_dt = cpu_port_rate(workload, cpu_agents, cpu_steps)
-        py_agents, py_steps = (n, 50) if workload == "c2" else (1 << 13, 4)
-        py_rate = python_port_rate(workload, py_agents, py_steps)
-        ref = reference_rate(workload, min(n, 1 << 12), 4)
-        if ref is not None:
-            cpu_baseline = {"value": ref[0], "unit": "agent-steps/s", "cores": 1, "kind": "reference",
-                            "sample": f"4 vector steps x {min(n, 1 << 12)} agents ({ref[1]:.1f} s); {ref[2]}",
-                            "c_port_value": cpu_rate, "c_port_cores": os.cpu_count() or 1,
-                            "c_port_sample": f"{cpu_steps} vector steps x {cpu_agents} agents, C port of the reference loop ({cpu_dt:.1f} s)",
-                            "python_port_value": py_rate, "python_port_cores": 1,
-                            "python_port_sample": f"{py_steps} vector steps x {py_agents} agents, NumPy/Python restatement"}
-        else:
-            cpu_baseline = {"value": cpu_rate, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
-                        "sample": f"{cpu_steps} vector steps x {cpu_agents} agents, C port of the reference loop ({cpu_dt:.1f} s)",
-                        "python_port_value": py_rate, "python_port_cores": 1,
-                        "python_port_sample": f"{py_steps} vector steps x {py_agents} agents, NumPy/Python restatement (per-agent Python learn loop like the reference)"}
+        base = cpu_baselines_subprocess(workload)
+        if base is not None and "single_thread" in base:
+            cpu_baseline = {"value": base["single_thread"]["value"], "unit": "agent-steps/s", "cores": 1, "kind": "reference",
+                            "sample": base["single_thread"]["sample"], **{k: v for k, v in base.items() if k != "single_thread"}}
+        elif base is not None:
+            cpu_baseline = {"value": base["c_port"]["value"], "unit": "agent-steps/s", "cores": base["c_port"]["cores"], "kind": "port",
+                            "sample": base["c_port"]["sample"], **{k: v for k, v in base.items() if k != "c_port"}}
     cfg = {"workload": f"{workload}: {desc}" + (f", one replica per GPU, Q-delta all-reduce every {SYNC_EVERY} steps (BASELINE config 5)" if world > 1 else ""),
            "states": s, "actions": a, "agents_per_gpu": n, "agents": n * world, "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM,
            "table_init": "uniform[0,1)" if workload != "c2" else "zeros", "rng": "on-device counter stream",
            "steps_per_launch": per_launch,
-           "timing": "CUDA events around the K timed steps (max over ranks); no L2 flush: the working set (256 MB of row blocks + "
-                     "~60 MB of per-agent arrays) is larger than the 126 MB L2",
-           "grid_blocks": grid_blocks, "td_update_form_at_end_of_window": fused_form, "timed_window": f"vector steps {W}..{W + K} of the run",
-           "td_update_form_calibration": calibration, "td_update_form_reprobes": reprobes or None, "late_training": late}
+           "timing": "CUDA events around the K timed steps (max over ranks); no L2 flush: every vector step touches the dense table (64 MB at "
+                     "config 3) plus ~90 MB of per-agent / per-position arrays, more than the 126 MB L2 (ncu: L2 hit rate 65 %)",
+           "grid_blocks": grid_blocks, "td_update_form": fused_form, "timed_window": f"vector steps {W}..{W + K} of the run",
+           "warmup_requested": args.warmup, "warmup_used": W, "late_training": late}
     out = {
         "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": cfg, "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
         "episodes": episodes,
     }
+    if value_long is not None:
+        out["value_long"] = value_long
+    if parity is not None:
+        out["multi_gpu_parity"] = parity.get("result", "FAIL")
+        out["multi_gpu_parity_detail"] = parity
     if atomics is not None:
         out["atomics_mode"] = atomics
     if cpu_baseline is not None:
@@ -721,12 +924,14 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=40)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "_cpu"])
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the bounded run of the sharded 100M-state table")
     ap.add_argument("--no-late", action="store_true", help="N = 1: skip the extra measurement after 256 vector steps")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "_cpu":
+        out = cpu_baselines(args.workload or "c3", quick=os.environ.get("BENCH_QUICK_CPU", "0") == "1")
+    elif args.impl == "reference":
         out = run_reference(args)
     else:
         world = int(os.environ.get("WORLD_SIZE", "1"))

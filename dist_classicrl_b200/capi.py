@@ -97,6 +97,7 @@ SIGNATURES = {
     "qe_fused_form": (i32, [vp]),
     "qe_set_fused_form": (C.c_int, [vp, i32]),
     "qe_fused_phase_ns": (i32, [vp, vp, i32]),
+    "qe_debug_gather_gbs": (C.c_double, [vp]),
     "qe_debug_gridsync_us": (C.c_double, [vp, i32]),
     "qe_debug_counters": (C.c_int, [vp, vp, i32]),
     "qe_build_info": (C.c_char_p, []),

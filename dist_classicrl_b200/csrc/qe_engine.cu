@@ -330,6 +330,56 @@ double qe_debug_gridsync_us(qe_engine_t* e, int32_t iters) {
     if (cudaMemcpy(&ns, d_out, sizeof(ns), cudaMemcpyDeviceToHost) != cudaSuccess) return -1.0;
     return (double)ns / 1e3 / iters;
 }
+}  // extern "C"
+// random row gather over the engine's own table, no dependencies: LPR lanes fetch one row (one 32-byte sector each),
+// `inflight` rows per lane group in flight
+template <int LPR>
+static __global__ void __launch_bounds__(256) gather_probe_kernel(const float* __restrict__ q, uint32_t rows, int ld, int per_thread, uint32_t seed, float* out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t grp = tid / LPR, l = tid % LPR;
+    float acc = 0.f;
+    for (int it = 0; it < per_thread; it += 4) {
+        F8 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_row8(q + (size_t)__umulhi(fmix32((grp * 7919u + (uint32_t)(it + u)) ^ seed), rows) * ld + 8 * l);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += v[u].v[0] + v[u].v[7];
+    }
+    if (acc == 12345.678f) out[0] = acc;
+}
+extern "C" {
+/* What the memory system allows for this engine's dominant access pattern: GB/s of random whole-row gathers over THIS
+ * table (no dependencies, four rows in flight per lane group).  bench.py reports it as roofline.gather_peak beside the
+ * copy peak.  Synchronous; ~1 ms. */
+double qe_debug_gather_gbs(qe_engine_t* e) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (cudaSetDevice(e->device) != cudaSuccess || e->A > 32) return -1.0;
+    const int blocks = e->sms * 8, per = 64;
+    const uint32_t rows = (uint32_t)std::min<int64_t>(e->S, 0x7FFFFFFF);
+    float* out = (float*)e->phase_ns;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1.0;
+    float best = 1e30f;
+    for (int r = 0; r < 4; ++r) {
+        cudaEventRecord(a);
+        switch (e->lpr) {
+            case 1: gather_probe_kernel<1><<<blocks, 256>>>(e->q_real, rows, e->ld, per, 11u + r, out); break;
+            case 2: gather_probe_kernel<2><<<blocks, 256>>>(e->q_real, rows, e->ld, per, 11u + r, out); break;
+            default: gather_probe_kernel<4><<<blocks, 256>>>(e->q_real, rows, e->ld, per, 11u + r, out); break;
+        }
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { best = -1.0f; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms > 0.f && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    e->launches += 4;
+    if (best <= 0.f) return -1.0;
+    const double rows_read = (double)blocks * 256 / e->lpr * per;
+    return rows_read * e->lpr * 32 / best / 1e6;
+}
 int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap) {
     std::lock_guard<std::mutex> lk(e->mu);
     uint64_t h[48];

@@ -534,11 +534,8 @@ class ReplicatedQLearning:
         # carry_over: the period counts vector steps ACROSS run_steps calls (a caller that advances one step per call
         # still merges every sync_every steps) instead of merging at the end of every call
         self.carry_over, self._since_sync = bool(carry_over), 0
-        # Merged replicas learn world_size times as fast, so agents herd onto the same rows sooner: the per-step sort is
-        # the form of the exact update whose cost does not grow with the crowd, and a form that is the same on every rank
-        # keeps the ranks in step at the all-reduce (QE_SORTED in the environment overrides).
-        if transport.world_size > 1 and "QE_SORTED" not in os.environ:
-            capi.check(capi.lib().qe_set_fused_form(algo.handle, 1))
+        # (Round 1 pinned the per-step-sort form here so that ranks probing different forms would not wait for each other
+        # at the all-reduce; the engine's default form, the target pipeline, is one form on every rank.)
         self.rebase()
 
     def _stream(self):

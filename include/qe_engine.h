@@ -239,6 +239,9 @@ int qe_set_fused_form(qe_engine_t* e, int32_t form);
  * of the first 10 vector steps the time after phase A (select + env step + writer registration), after phase B1 (TD
  * update, first pass) and after phase B2 (TD update, deferred agents).  Returns the number of values written. */
 int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap);
+/* GB/s of dependency-free random whole-row gathers over this table (the ceiling of the engine's dominant access pattern;
+ * bench.py: roofline.gather_peak) */
+double qe_debug_gather_gbs(qe_engine_t* e);
 /* development aid: microseconds per grid-wide barrier at the fused loop's launch shape (cooperative launch, 4 CTAs/SM) */
 double qe_debug_gridsync_us(qe_engine_t* e, int32_t iters);
 /* development aid: counters of the sorted loop's phase Q accumulated since the last reset (see qe_sorted.cuh) */
