@@ -65,4 +65,9 @@ def test_our_arm_prints_the_full_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1 and cb["sample"]
     assert d["atomics_mode"]["value"] > d["value"]  # dropping the ordering guarantee is never slower
-    assert d["config"]["td_update_form_calibration"]["picked"] in ("writer lists", "per-step sort")
+    assert d["config"]["td_update_form"] == "target pipeline" and r["kernel"].startswith("fused_pipe_kernel")
+    assert d["config"]["warmup_requested"] == 3 and d["config"]["warmup_used"] == d["warmup"]
+    vl = d["value_long"]
+    assert 0 < vl["value"] and vl["vector_steps"].startswith("8..") and len(vl["ms_per_step_by_32_step_window"]) >= 15
+    assert r["gather_peak"]["value"] > r["achieved"]  # dependency-free gathers over the same table bound the loop from above
+    assert "multiprocessing" in cb and cb["mpi"]["value"] is None
