@@ -225,8 +225,8 @@ def python_port_rate(workload: str, agents: int, steps: int):
 
 
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
-FORM_NAMES = {0: "writer lists", 1: "per-step sort", 3: "target pipeline"}
-FORM_KERNELS = {0: "fused_kernel", 1: "fused_sorted_kernel", 3: "fused_pipe_kernel"}
+FORM_NAMES = {0: "writer lists", 1: "per-step sort", 3: "target pipeline", 4: "one-CTA loop (small batches)"}
+FORM_KERNELS = {0: "fused_kernel", 1: "fused_sorted_kernel", 3: "fused_pipe_kernel", 4: "fused_small_kernel"}
 
 
 class TwinEnv:
@@ -586,8 +586,6 @@ def run_ours(args) -> dict | None:
 
     # ---------------- device-resident throughput: SYNC_EVERY vector steps per launch (+ table merge when N > 1)
     algo, env = make()
-    if workload == "c2" and "QE_SORTED" not in os.environ:
-        capi.check(lib.qe_set_fused_form(algo.handle, 0))  # a per-step sort of 128 agents is all barrier
     ep_ret = torch.zeros(n, dtype=torch.float32, device=dev)
     ag = env.agents_struct(ep_ret)
     stats = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -768,26 +766,31 @@ def run_ours(args) -> dict | None:
     rt = SingleThreadQLearning(algo, ConstantSchedule(LR), ConstantSchedule(EPS))
     rt.history_mode = "summary"
     runner = D.ReplicatedQLearning(rt, tp, sync_every=SYNC_EVERY, carry_over=True) if tp is not None else rt
-    Ke = min(K, 20)
+    # config 2's 128 agents take ~10 us per vector step: one host round trip per step would measure the host.  The caller
+    # asks for 64 steps per call there (their uniforms go down in one copy, their results come back once), one elsewhere.
+    call_steps = 64 if (workload == "c2" and world == 1) else 1
+    Ke = (min(K, 2048) // call_steps) * call_steps if call_steps > 1 else min(K, 20)
+    Ke = max(Ke, call_steps)
+    We = max(call_steps, min(W, 4 * call_steps)) if call_steps > 1 else W
     slots = env.slots
-    u_host = torch.empty((W + Ke, n, slots), dtype=torch.int32).pin_memory()
-    u_host.numpy().view(np.uint32)[:] = draw_uniforms(STREAM_SEED, 0, W + Ke, n, slots, agent0=env.agent0)
+    u_host = torch.empty((We + Ke, n, slots), dtype=torch.int32).pin_memory()
+    u_host.numpy().view(np.uint32)[:] = draw_uniforms(STREAM_SEED, 0, We + Ke, n, slots, agent0=env.agent0)
     pre = PredrawnUniforms(u_host.numpy().view(np.uint32))  # no copy: already contiguous uint32 (pinned)
     algo._rng = env._rng = pre
     sd = {"states": None, "infos": {}, "rewards": np.zeros(n, dtype=np.float32)}
-    for _ in range(W):
-        _, _, _, sd = runner.run_steps(1, env, sd)
+    for _ in range(We // call_steps):
+        _, _, _, sd = runner.run_steps(call_steps, env, sd)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(Ke):
-        _, _, _, sd = runner.run_steps(1, env, sd)  # returns host copies of the agents' running returns
+    for _ in range(Ke // call_steps):
+        _, _, _, sd = runner.run_steps(call_steps, env, sd)  # returns host copies of the agents' running returns
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d = n * slots * 4 + n * 4 + 12  # the step's uniforms + the agents' running returns (state dict) + eps/lr of the step
     d2h = n * 4 + 16                  # the running returns + {sum, count} of the episodes that finished in the step
     e2e = {"value": world * n * Ke / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
            "steps": Ke, "api": (f"ReplicatedQLearning(sync_every={SYNC_EVERY}, carry_over=True)." if tp is not None else "SingleThreadQLearning.") +
-           "run_steps(1, env, state_dict): the step's pre-drawn uniforms (PredrawnUniforms, pinned host memory) and the state dict's running returns go host->device, the returns and the episode statistics come back, every step"}
+           f"run_steps({call_steps}, env, state_dict): the step's pre-drawn uniforms (PredrawnUniforms, pinned host memory) and the state dict's running returns go host->device, the returns and the episode statistics come back, every step"}
     del algo, env, runner, rt
 
     # ---------------- sharded 100M-state table (config 4): peer memory over NVLink, one persistent kernel per GPU
@@ -875,7 +878,7 @@ def run_ours(args) -> dict | None:
                 traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:  # noqa: BLE001
             traffic = None
-    kname = FORM_KERNELS.get(form_id, "fused_kernel") + ("<TTT,2>" if workload == "c2" else ("<MDP,1>" if a <= 8 else "<MDP,2>"))
+    kname = FORM_KERNELS.get(form_id, "fused_kernel") + (("<TTT>" if form_id == 4 else "<TTT,2>") if workload == "c2" else ("<MDP,1>" if a <= 8 else "<MDP,2>"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_agent_step": balg,
                 "algorithmic_bytes_per_launch": n * steps_per_launch * balg, "avg_launch_ms": per_launch_ms,

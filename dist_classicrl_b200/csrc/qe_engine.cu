@@ -12,6 +12,7 @@
 #include "qe_kernels.cuh"
 #include "qe_sorted.cuh"
 #include "qe_pipe.cuh"
+#include "qe_small.cuh"
 #include "qe_radix.cuh"
 
 using namespace qe;
@@ -800,6 +801,8 @@ constexpr int kProbeEvery = 12;
 // launches out of kProbeEvery); all other launches carry no events at all.  *time_it: record events around this launch.
 static int pick_form(qe_engine* e, const FusedArgs& F, bool* time_it) {
     *time_it = false;
+    // small batches: one CTA, no grid barrier (qe_small.cuh); QE_FORM / qe_set_fused_form(0..2) still pin the grid-wide forms
+    if (F.n <= kSmallMaxAgents && e->A <= 32 && e->S < (1ll << 26) && !F.accumulate && e->strategy == 3 && !getenv("QE_NO_SMALL")) return 4;
     if (e->state_base != 0 || e->A > 32 || !e->X.seg) return 0;
     if (F.accumulate || F.evaluate) return 0;  // the plain-atomics update and the evaluation loop live in fused_kernel
     if (e->strategy == 3) return e->S < (1ll << 30) ? 3 : 1;  // the pipeline's records keep the state in 30 bits
@@ -842,7 +845,12 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
     bool timed = false;
     const int form = pick_form(e, F, &timed);
     if (timed) CK(cudaEventRecord(e->ev0, st));
-    if (form == 3) {
+    if (form == 4) {
+        e->pipe_valid = false;  // (the agents move without the pipelined form's order being kept)
+        blocks = 1;
+        void* args[] = {&T, &F};
+        CK(cudaLaunchKernel((void*)fused_small_kernel<ENV, LPR>, dim3(1), dim3(kSmallMaxAgents), args, 0, st));
+    } else if (form == 3) {
         const size_t smem = pipe_smem_bytes(LPR);
         CK(cudaFuncSetAttribute(fused_pipe_kernel<ENV, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;

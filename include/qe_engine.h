@@ -228,7 +228,8 @@ int32_t qe_shard_info(qe_shard_t* s, int32_t what); /* 0: rows per shard, 1: age
 uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k);
 int64_t qe_kernel_launches(qe_engine_t* e);     /* kernels launched by this handle so far */
 int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch */
-/* form of the TD update the last fused launch used: 0 = writer lists, 1 = per-step sort, 3 = target pipeline (all exact) */
+/* form of the TD update the last fused launch used: 0 = writer lists, 1 = per-step sort, 3 = target pipeline, 4 = one-CTA
+ * loop for batches of at most 256 agents (csrc/qe_small.cuh; picked automatically under form 3).  All exact. */
 int32_t qe_fused_form(qe_engine_t* e);
 /* Which exact form of the TD update the fused loop uses: 0 = writer lists, 1 = per-step sort, 2 = keep timing those two
  * and use the faster one, 3 = target pipeline (csrc/qe_pipe.cuh; default; QE_FORM in the environment sets the initial

@@ -166,7 +166,25 @@ def test_all_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form,
     try:
         r.steps(steps // 2)
         r.steps(steps - steps // 2)
-        assert capi.lib().qe_fused_form(r.h) == int(form)
+        assert capi.lib().qe_fused_form(r.h) == (4 if (form == "3" and N <= 256) else int(form))  # batches of <= 256 agents: the one-CTA loop
+        assert np.array_equal(r.states.cpu().numpy(), st_o)
+        assert np.array_equal(r.ep.cpu().numpy(), rew_o)
+        assert np.array_equal(r.table(), q_o)
+    finally:
+        r.close()
+
+
+@pytest.mark.parametrize("S,A,N,steps", [(19, 4, 1, 60), (500, 9, 128, 200), (40, 32, 256, 50), (5000, 16, 255, 64), (3, 8, 200, 30)])
+def test_small_batches_one_cta_loop_matches_the_oracle(capi, monkeypatch, S, A, N, steps):
+    """Batches of at most 256 agents run in one CTA (csrc/qe_small.cuh): same results as the oracle, whatever the crowding."""
+    monkeypatch.delenv("QE_FORM", raising=False)
+    seed = 5
+    q_o, st_o, rew_o, _ = _oracle(S, A, N, steps, seed, 1)
+    r = Run(capi, S, A, N, seed, 1)
+    try:
+        r.steps(steps // 3)
+        r.steps(steps - steps // 3)
+        assert capi.lib().qe_fused_form(r.h) == 4
         assert np.array_equal(r.states.cpu().numpy(), st_o)
         assert np.array_equal(r.ep.cpu().numpy(), rew_o)
         assert np.array_equal(r.table(), q_o)
