@@ -115,10 +115,17 @@ class OptimalQLearningBase:
         may be modified in place -- it is uploaded again before the next device operation."""
         if self._host is None:
             self._host = np.zeros((self.state_size, self.action_size), dtype=np.float32)
+        self._refresh_host()
+        self._host_dirty = True  # the caller may write through the returned array
+        return self._host
+
+    def _refresh_host(self) -> NDArray[np.float32]:
+        """The mirror with the device contents, WITHOUT marking it dirty (read-only accessors, ``save``)."""
+        if self._host is None:
+            self._host = np.zeros((self.state_size, self.action_size), dtype=np.float32)
         if not self._host_valid:
             capi.check(self._lib.qe_table_download_host(self._h, _ptr(self._host)))
             self._host_valid = True
-        self._host_dirty = True
         return self._host
 
     @q_table.setter
@@ -160,23 +167,25 @@ class OptimalQLearningBase:
         self._device_wrote()
 
     # ------------------------------------------------------------------ accessors (QLO:100-261)
+    # (read-only accessors go through _refresh_host: they return copies / scalars and do not force a re-upload of the table;
+    #  the reference returns views of its array for slices -- callers that write through them must use q_table)
     def get_q_value(self, state: int, action: int) -> float:
-        return self.q_table[state, action]
+        return self._refresh_host()[state, action]
 
     def get_q_values(self, states, actions):
-        return self.q_table[states, actions]
+        return self._refresh_host()[states, actions]
 
     def get_state_q_values(self, state: int):
-        return self.q_table[state]
+        return self._refresh_host()[state].copy()
 
     def get_states_q_values(self, states):
-        return self.q_table[states]
+        return self._refresh_host()[states]
 
     def get_action_q_values(self, action: int):
-        return self.q_table[:, action]
+        return self._refresh_host()[:, action].copy()
 
     def get_actions_q_values(self, actions):
-        return self.q_table[:, actions]
+        return self._refresh_host()[:, actions]
 
     def set_q_value(self, state: int, action: int, value: float) -> None:
         self.q_table[state, action] = value
@@ -188,7 +197,7 @@ class OptimalQLearningBase:
         np.add.at(self.q_table, (states, actions), values)  # duplicates accumulate (T-QLO:64-82)
 
     def save(self, filename: str) -> None:
-        np.save(filename, self.q_table)
+        np.save(filename, self._refresh_host())
 
     def load(self, filename: str) -> None:
         """Resume from a table written by :meth:`save` (or by the reference's ``save``, QLO:252-261); an fp64 table
@@ -227,6 +236,21 @@ class OptimalQLearningBase:
         n = len(states)
         return self._choose(states, exploration_rate, deterministic, action_masks, self._variant(n, deterministic, action_masks is not None))
 
+    @staticmethod
+    def _checked(idx, size: int, what: str) -> np.ndarray:
+        """Host index array as int32 inside [0, size): negative values wrap NumPy-style, anything else out of range raises
+        IndexError like the reference's ``q_table[idx]`` would -- the kernels index HBM directly and do not check."""
+        arr = np.asarray(idx)
+        if arr.dtype.kind not in "iu":
+            arr = arr.astype(np.int64)
+        if arr.size and (arr.min() < 0 or arr.max() >= size):
+            arr = arr.astype(np.int64, copy=True)
+            arr[arr < 0] += size
+            if arr.size and (arr.min() < 0 or arr.max() >= size):
+                bad = arr[(arr < 0) | (arr >= size)][0]
+                raise IndexError(f"{what} index {int(bad)} is out of bounds for size {size}")
+        return np.ascontiguousarray(arr, dtype=np.int32)
+
     def _choose(self, states, eps, deterministic, action_masks, variant):
         self._before_device_op()
         n = len(states)
@@ -263,7 +287,7 @@ class OptimalQLearningBase:
             capi.check(self._lib.qe_select(self._h, _ptr(st), _ptr(bits), _ptr(mbytes), _ptr(u_dev), slots, seed, t, 0, thresh,
                                            int(deterministic), empty_all, _ptr(out), n, C.c_void_p(stream)))
             return out
-        st = np.ascontiguousarray(states, dtype=np.int32)
+        st = self._checked(states, self.state_size, "state")
         bits = mbytes = None
         if action_masks is not None:
             if a <= 32:
@@ -286,7 +310,7 @@ class OptimalQLearningBase:
         return out
 
     def _rows(self, states) -> np.ndarray:
-        st = np.ascontiguousarray(states, dtype=np.int32)
+        st = self._checked(states, self.state_size, "state")
         rows = np.empty((st.shape[0], self.action_size), dtype=np.float32)
         capi.check(self._lib.qe_gather_rows_host(self._h, _ptr(st), _ptr(rows), st.shape[0]))
         return rows
@@ -419,8 +443,8 @@ class OptimalQLearningBase:
                 bits = masks_to_bits(next_action_masks, a)
             else:
                 mbytes = np.ascontiguousarray(np.asarray(next_action_masks) != 0, dtype=np.uint8)
-        args = (np.ascontiguousarray(states, dtype=np.int32), np.ascontiguousarray(actions, dtype=np.int32),
-                np.ascontiguousarray(rewards, dtype=np.float32), np.ascontiguousarray(next_states, dtype=np.int32),
+        args = (self._checked(states, self.state_size, "state"), self._checked(actions, a, "action"),
+                np.ascontiguousarray(rewards, dtype=np.float32), self._checked(next_states, self.state_size, "next state"),
                 np.ascontiguousarray(terminated, dtype=np.uint8))
         for arr in args[1:]:
             if arr.shape[0] != n:  # zip(strict=True) in QLO:801-808

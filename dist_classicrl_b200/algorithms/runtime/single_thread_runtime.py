@@ -24,7 +24,10 @@ class SingleThreadQLearning(BaseRuntime):
     def close_training(self) -> None:
         return None
 
-    def run_steps(self, steps: int, env, curr_state_dict: dict | None = None, *, trace: dict | None = None):
+    def run_steps(self, steps: int, env, curr_state_dict: dict | None = None, *, trace: dict | None = None, _mean: bool = True):
+        """``_mean=False`` (internal: callers that run a window of a longer ``run_steps``, e.g. ``ReplicatedQLearning``)
+        skips the mean, so that a window in which no episode ends does not raise the reference's ZeroDivisionError
+        (STR:67) in the middle of a run that does finish episodes."""
         reward_history: list[Any] = []
         if curr_state_dict is None:
             states, infos = env.reset()
@@ -34,14 +37,16 @@ class SingleThreadQLearning(BaseRuntime):
         if self._can_fuse(env):
             reward_history = self._run_fused(env, steps, agent_rewards, trace=trace)
             states = env._obs_lazy()
-            if self.history_mode == "full":
+            if not _mean:
+                mean = 0.0
+            elif self.history_mode == "full":
                 mean = sum(reward_history) / len(reward_history)  # ZeroDivisionError if no episode ended (STR:67)
             else:
                 mean = self.last_episode_sum / self.last_episode_count if self.last_episode_count else 0.0
         else:
             for _ in range(steps):
                 states, infos = self.run_single_step(env, states, agent_rewards, reward_history)
-            mean = sum(reward_history) / len(reward_history)
+            mean = sum(reward_history) / len(reward_history) if _mean else 0.0
         return (
             mean,
             reward_history,

@@ -11,6 +11,7 @@ import os
 
 from dist_classicrl_b200 import build as _build
 
+QE_ABI_VERSION = 2  # include/qe_engine.h; checked against the library at load
 QE_OK = 0
 QE_ERR_ARG, QE_ERR_CUDA, QE_ERR_INVALID_MOVE, QE_ERR_EMPTY, QE_ERR_TIMEOUT = -1, -2, -3, -4, -5
 QE_ENV_MDP, QE_ENV_TTT, QE_ENV_BANDIT = 0, 1, 2
@@ -40,6 +41,7 @@ class QeRun(C.Structure):
 SIGNATURES = {
     "qe_create": (C.c_int, [i64, i32, f32, i32, C.POINTER(vp)]),
     "qe_destroy": (C.c_int, [vp]),
+    "qe_abi_version": (C.c_int, []),
     "qe_last_error": (C.c_char_p, []),
     "qe_set_last_error": (C.c_int, [C.c_int, C.c_char_p]),
     "qe_shard_slab_bytes": (i64, [i64, i32, i32, i32]),
@@ -124,11 +126,17 @@ def lib():
         try:
             _build.build()
         except Exception as exc:  # noqa: BLE001
-            if not os.path.exists(path):
-                raise ImportError(
-                    f"libqe_b200.so is missing and could not be built ({exc}); the B200 engine has no CPU fallback"
-                ) from exc
+            # no stale binary behind newer sources: its struct layouts and signatures may not be the ones bound below
+            raise ImportError(
+                f"libqe_b200.so is missing or older than its sources and could not be rebuilt ({exc}); the B200 engine has no CPU fallback"
+            ) from exc
     handle = C.CDLL(path)
+    try:
+        got = int(handle.qe_abi_version())
+    except AttributeError:
+        got = -1
+    if got != QE_ABI_VERSION:
+        raise ImportError(f"{path} was built for ABI version {got}, this binding expects {QE_ABI_VERSION}: rebuild with python -m dist_classicrl_b200.build --force")
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res

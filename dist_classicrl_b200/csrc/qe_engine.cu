@@ -35,6 +35,15 @@ extern "C" int qe_set_last_error(int code, const char* msg) {  // for the librar
         if (_e != cudaSuccess) return fail(QE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+// the engine-less entry points launch on the device that owns their buffers (a process that drives several GPUs may
+// have another device current)
+static int use_device_of(const void* p) {
+    cudaPointerAttributes at;
+    if (p && cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) CK(cudaSetDevice(at.device));
+    else (void)cudaGetLastError();
+    return QE_OK;
+}
+
 struct qe_engine {
     int64_t S = 0;
     int A = 0, ld = 0, lpa = 0, lpr = 0, device = 0, sms = 0;  // lpa: 16-byte lanes per row (select_kernel); lpr: 32-byte sectors per row
@@ -86,15 +95,18 @@ static Table local_table(const qe_engine* e) {  // rows indexed from 0 (whole-ta
 static int lanes_per_agent(int A) { return A <= 4 ? 1 : (A <= 8 ? 2 : (A <= 16 ? 4 : 8)); }
 static int sectors_per_row(int A) { return A <= 8 ? 1 : (A <= 16 ? 2 : 4); }
 
+#define QE_FREE(p) do { cudaFree(p); (p) = nullptr; } while (0)
 static int ensure_agents(qe_engine* e, int n) {
     if (n <= e->cap) return QE_OK;
     int cap = 1024;
     while (cap < n) cap <<= 1;
     CK(cudaDeviceSynchronize());
-    cudaFree(e->T.node); cudaFree(e->T.slot); cudaFree(e->T.tr_p); cudaFree(e->tr_a); cudaFree(e->tr_r); cudaFree(e->delta);
-    cudaFree(e->T.later_buf);
+    // everything is released and forgotten first: if an allocation below fails, no pointer dangles, the capacity is 0 and
+    // the next call starts over (qe_destroy frees whatever did get allocated)
+    e->cap = 0;
+    QE_FREE(e->T.node); QE_FREE(e->T.slot); QE_FREE(e->T.tr_p); QE_FREE(e->tr_a); QE_FREE(e->tr_r); QE_FREE(e->delta);
+    QE_FREE(e->T.later_buf); QE_FREE(e->T.rec); QE_FREE(e->T.dmask); QE_FREE(e->T.smask);
     CK(cudaMalloc(&e->T.later_buf, cap));
-    cudaFree(e->T.rec); cudaFree(e->T.dmask); cudaFree(e->T.smask);
     CK(cudaMalloc(&e->T.smask, sizeof(uint32_t) * (cap / 32)));
     CK(cudaMalloc(&e->T.rec, sizeof(uint32_t) * 8 * (size_t)cap));
     CK(cudaMalloc(&e->T.dmask, sizeof(uint32_t) * (cap / 32)));
@@ -107,8 +119,8 @@ static int ensure_agents(qe_engine* e, int n) {
     CK(cudaMemset(e->T.slot, 0, sizeof(uint64_t) * cap));
     {
         SortedScratch& X = e->X;
-        for (int b = 0; b < 2; ++b) { cudaFree(X.key[b]); cudaFree(X.val[b]); }
-        cudaFree(X.rank); cudaFree(X.targ); cudaFree(X.mhist); cudaFree(X.rrec); cudaFree(X.rmask); cudaFree(X.hmask); cudaFree(X.hrec);
+        for (int b = 0; b < 2; ++b) { QE_FREE(X.key[b]); QE_FREE(X.val[b]); }
+        QE_FREE(X.rank); QE_FREE(X.targ); QE_FREE(X.mhist); QE_FREE(X.rrec); QE_FREE(X.rmask); QE_FREE(X.hmask); QE_FREE(X.hrec);
         CK(cudaMalloc(&X.hrec, sizeof(uint32_t) * 4 * (size_t)cap));
         for (int b = 0; b < 2; ++b) {
             CK(cudaMalloc(&X.key[b], sizeof(int32_t) * cap));
@@ -125,9 +137,8 @@ static int ensure_agents(qe_engine* e, int n) {
     }
     {
         PipeScratch& P = e->P;
-        for (int b = 0; b < 2; ++b) { cudaFree(P.kv[b]); P.kv[b] = nullptr; }
-        cudaFree(P.tw); cudaFree(P.rec); cudaFree(P.pos);
-        P.tw = nullptr; P.rec = nullptr; P.pos = nullptr;
+        for (int b = 0; b < 2; ++b) QE_FREE(P.kv[b]);
+        QE_FREE(P.tw); QE_FREE(P.rec); QE_FREE(P.pos);
         e->pipe_valid = false;
         e->pipe_sorted_n = 0;  // the order kv[] described is gone with the buffers: seg[] starts from all-empty again
         if (P.seg) CK(cudaMemset(P.seg, 0, sizeof(uint2) * (size_t)e->S));
@@ -213,12 +224,27 @@ const char* qe_last_error(void) { return g_err; }
 const char* qe_build_info(void) { return "libqe_b200 sm_100a (" __DATE__ " " __TIME__ ")"; }
 uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k) { return stream_u32(seed, t, i, k); }
 
+static int create_impl(qe_engine* e, int64_t num_states, int32_t num_actions, float discount_factor, int32_t device);
+int qe_abi_version(void) { return QE_ABI_VERSION; }
 int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, int32_t device, qe_engine_t** out) {
     if (!out || num_states <= 0 || num_actions <= 0) return fail(QE_ERR_ARG, "state_size and action_size must be positive");
     if (num_states >= (1ll << 31)) return fail(QE_ERR_ARG, "state_size must be < 2^31");
     CK(cudaSetDevice(device));
     qe_engine* e = new (std::nothrow) qe_engine();
     if (!e) return fail(QE_ERR_ARG, "out of host memory");
+    e->device = device;
+    const int rc = create_impl(e, num_states, num_actions, discount_factor, device);
+    if (rc) {  // whatever was allocated so far goes back (cudaFree(nullptr) is a no-op); the error message stays
+        char keep[512];
+        snprintf(keep, sizeof(keep), "%s", g_err);
+        qe_destroy(e);
+        snprintf(g_err, sizeof(g_err), "%s", keep);
+        return rc;
+    }
+    *out = e;
+    return QE_OK;
+}
+static int create_impl(qe_engine* e, int64_t num_states, int32_t num_actions, float discount_factor, int32_t device) {
     e->S = num_states;
     e->A = num_actions;
     e->gamma = discount_factor;
@@ -268,10 +294,7 @@ int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, in
     CK(cudaMemset(e->T.spill_next, 0, 2 * sizeof(int)));
     CK(cudaMalloc(&e->phase_ns, 48 * sizeof(uint64_t)));
     CK(cudaMemset(e->phase_ns, 0, 48 * sizeof(uint64_t)));
-    int rc = ensure_agents(e, 1024);
-    if (rc) { qe_destroy(e); return rc; }
-    *out = e;
-    return QE_OK;
+    return ensure_agents(e, 1024);
 }
 
 int qe_destroy(qe_engine_t* e) {
@@ -441,6 +464,7 @@ int qe_radix_encode(const int32_t* vectors, const int64_t* radix_host, int32_t d
     int rc = radix_spec(R, nullptr, radix_host, dims);
     if (rc) return rc;
     if (n <= 0) return QE_OK;
+    if ((rc = use_device_of(vectors)) != QE_OK) return rc;
     radix_encode_kernel<<<radix_grid(n), 256, 256 * (dims | 1) * sizeof(int32_t), (cudaStream_t)stream>>>(vectors, R, (long long*)out, (long long)n);
     CK(cudaGetLastError());
     return QE_OK;
@@ -454,6 +478,7 @@ int qe_radix_decode(const int64_t* indices, const int64_t* nvec_host, const int6
     for (int d = 0; d < dims; ++d)
         if (R.radix[d] == 0 || R.nvec[d] == 0) return fail(QE_ERR_ARG, "radix: zero radix / nvec entry");
     if (n <= 0) return QE_OK;
+    if ((rc = use_device_of(indices)) != QE_OK) return rc;
     radix_decode_kernel<<<radix_grid(n), 256, 256 * (dims | 1) * sizeof(int32_t), (cudaStream_t)stream>>>((const long long*)indices, R, out, (long long)n);
     CK(cudaGetLastError());
     return QE_OK;
@@ -737,6 +762,7 @@ int qe_table_merge_dense(qe_engine_t* e, float* base_inout, const float* delta_s
 int qe_ttt_reset(uint32_t* boards, int32_t* states_out, uint32_t* mask_bits_out, const uint32_t* uniforms, int32_t slots,
                  uint32_t stream_seed, uint32_t t, uint32_t agent0, int32_t n, void* stream) {
     if (n <= 0) return QE_OK;
+    { int rc = use_device_of(boards); if (rc) return rc; }
     if (uniforms && slots < 5) return fail(QE_ERR_ARG, "TicTacToe needs 5 uniform slots");
     Uniforms U{uniforms, slots, stream_seed, t, agent0, stream_seed, t};
     ttt_reset_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boards, states_out, mask_bits_out, U, n);
@@ -761,6 +787,7 @@ int qe_mdp_reset(int32_t* states, uint32_t* mask_bits_out, int64_t num_states, i
                  void* stream) {
     if (n <= 0) return QE_OK;
     if (uniforms && slots < 4) return fail(QE_ERR_ARG, "the hash MDP needs 4 uniform slots");
+    { int rc = use_device_of(states); if (rc) return rc; }
     Uniforms U{uniforms, slots, stream_seed, t, agent0, stream_seed, t};
     mdp_reset_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(states, mask_bits_out, (uint32_t)num_states, num_actions,
                                                                      env_seed, U, n);
@@ -769,6 +796,7 @@ int qe_mdp_reset(int32_t* states, uint32_t* mask_bits_out, int64_t num_states, i
 }
 int qe_mdp_masks(const int32_t* states, uint32_t* mask_bits_out, int32_t num_actions, uint32_t env_seed, int32_t n, void* stream) {
     if (n <= 0) return QE_OK;
+    { int rc = use_device_of(states); if (rc) return rc; }
     mdp_masks_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(states, mask_bits_out, num_actions, env_seed, n);
     CK(cudaGetLastError());
     return QE_OK;
@@ -950,6 +978,15 @@ int qe_fused_steps(qe_engine_t* e, const qe_agents_t* ag, const qe_run_t* run, v
     }
     CK(cudaMemcpyAsync(e->d_thresh, run->explore_thresholds_host, sizeof(uint64_t) * run->steps, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->d_lr, run->learning_rates_host, sizeof(float) * run->steps, cudaMemcpyHostToDevice, st));
+    if (e->step > 0xFFFF0000u - (uint32_t)run->steps) {  // the 32-bit epoch that stamps the scratch of forms 0 and 1 is about to wrap: start it over
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemset(e->T.slot, 0, sizeof(uint64_t) * e->cap));
+        CK(cudaMemset(e->X.targ, 0, sizeof(uint64_t) * e->cap));
+        CK(cudaMemset(e->X.mhist, 0, sizeof(uint64_t) * e->cap));
+        if (e->X.seg) CK(cudaMemset(e->X.seg, 0, sizeof(uint32_t) * 4 * (size_t)e->S));
+        if (e->info_real) CK(cudaMemset(e->info_real, 0, sizeof(uint32_t) * (size_t)e->S * e->T.info_ld));
+        e->step = 0;
+    }
     FusedArgs F{};
     F.env_kind = ag->env_kind; F.n = n; F.steps = run->steps;
     F.st_a = ag->states; F.st_b = ag->states_scratch; F.envw = ag->env_words; F.ep_ret = ag->episode_returns;

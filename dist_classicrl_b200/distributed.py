@@ -572,14 +572,21 @@ class ReplicatedQLearning:
         history: list[float] = []
         state = curr_state_dict
         done = 0
+        ep_count, ep_sum = 0, 0.0  # summary mode: episode statistics accumulated over the windows
         while done < steps:
             k = min(self.sync_every - self._since_sync, steps - done)
-            _, hist, env, state = self.runtime.run_steps(k, env, state)
+            _, hist, env, state = self.runtime.run_steps(k, env, state, _mean=False)
             history.extend(hist)
+            ep_count += int(getattr(self.runtime, "last_episode_count", 0))
+            ep_sum += float(getattr(self.runtime, "last_episode_sum", 0.0))
             done += k
             self._since_sync += k
             if self._since_sync >= self.sync_every or (done == steps and not self.carry_over):
                 self.sync()
                 self._since_sync = 0
-        mean = float(np.mean(history)) if history else 0.0
+        self.runtime.last_episode_count, self.runtime.last_episode_sum = ep_count, ep_sum
+        if getattr(self.runtime, "history_mode", "full") == "full":
+            mean = float(sum(history) / len(history))  # the reference's contract for the WHOLE call: ZeroDivisionError if no episode ended (STR:67)
+        else:
+            mean = ep_sum / ep_count if ep_count else 0.0
         return mean, history, env, state

@@ -43,7 +43,9 @@ extern "C" {
 #define QE_LEARN_SEQUENTIAL 0 /* learn / learn_iter: exact per-agent order (QLO:770-817, 893-934) */
 #define QE_LEARN_ACCUMULATE 1 /* learn_vec / _learn_vec: snapshot bootstrap + np.add.at (QLO:853-891) */
 
+#define QE_ABI_VERSION 2 /* bumped whenever a struct of this header or an entry point's signature changes */
 typedef struct qe_engine qe_engine_t;
+int qe_abi_version(void); /* the QE_ABI_VERSION the loaded library was built with (bindings compare it at load) */
 
 /* ---- lifetime / table: replaces OptimalQLearningBase.__init__ and the q_table attribute (QLO:84-98, :80) ---- */
 int qe_create(int64_t num_states, int32_t num_actions, float discount_factor, int32_t device, qe_engine_t** out);
