@@ -225,7 +225,7 @@ def python_port_rate(workload: str, agents: int, steps: int):
 
 
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
-FORM_NAMES = {0: "writer lists", 1: "per-step sort", 3: "target pipeline", 4: "one-CTA loop (small batches)"}
+FORM_NAMES = {0: "writer lists", 1: "per-step sort", 3: "target pipeline", 4: "one-CTA loop (small batches)", 5: "one-pass pipeline"}
 FORM_KERNELS = {0: "fused_kernel", 1: "fused_sorted_kernel", 3: "fused_pipe_kernel", 4: "fused_small_kernel"}
 
 

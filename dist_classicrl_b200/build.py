@@ -10,7 +10,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc", "qe_engine.cu")
 SRC2 = os.path.join(PKG, "csrc", "qe_shard.cu")  # the peer-memory sharded table: its own translation unit (compiled in parallel)
-DEPS = [SRC, SRC2, os.path.join(PKG, "csrc", "qe_small.cuh"), os.path.join(PKG, "csrc", "qe_shard.cuh"), os.path.join(PKG, "csrc", "qe_pipe.cuh"), os.path.join(PKG, "csrc", "qe_kernels.cuh"), os.path.join(PKG, "csrc", "qe_common.cuh"), os.path.join(PKG, "csrc", "qe_sorted.cuh"), os.path.join(PKG, "csrc", "qe_radix.cuh"),
+DEPS = [SRC, SRC2, os.path.join(PKG, "csrc", "qe_small.cuh"), os.path.join(PKG, "csrc", "qe_shard.cuh"), os.path.join(PKG, "csrc", "qe_pipe.cuh"), os.path.join(PKG, "csrc", "qe_flow.cuh"), os.path.join(PKG, "csrc", "qe_kernels.cuh"), os.path.join(PKG, "csrc", "qe_common.cuh"), os.path.join(PKG, "csrc", "qe_sorted.cuh"), os.path.join(PKG, "csrc", "qe_radix.cuh"),
         os.path.join(os.path.dirname(PKG), "include", "qe_engine.h")]
 OUT = os.path.join(PKG, "_lib", "libqe_b200.so")
 

@@ -12,6 +12,7 @@
 #include "qe_kernels.cuh"
 #include "qe_sorted.cuh"
 #include "qe_pipe.cuh"
+#include "qe_flow.cuh"
 #include "qe_small.cuh"
 #include "qe_radix.cuh"
 
@@ -74,6 +75,7 @@ struct qe_engine {
     const int32_t* pipe_states = nullptr;
     int pipe_n = 0;
     int pipe_sorted_n = 0;   // agents of the order P.kv / P.seg still describe (0: none; seg[] is all-empty then)
+    int pipe_kind = 0;       // the form that left that order (3: target pipeline, 5: one-pass form; their records and buffers differ)
     int sorted_grid = 0;     // ghist was sized for this many blocks
     // The fused loop has two exact forms of the TD update: writer lists (qe_kernels.cuh; best while few agents share
     // a row) and the per-step sort (qe_sorted.cuh; best once agents herd).  Both give identical results, so the engine
@@ -285,7 +287,7 @@ static int create_impl(qe_engine* e, int64_t num_states, int32_t num_actions, fl
         e->X.passes = (bits + kRadixBits - 1) / kRadixBits;
     }
     e->strategy = getenv("QE_FORM") ? atoi(getenv("QE_FORM")) : (getenv("QE_SORTED") ? atoi(getenv("QE_SORTED")) : 3);
-    if (e->strategy < 0 || e->strategy > 3) e->strategy = 3;
+    if (e->strategy < 0 || e->strategy == 4 || e->strategy > 5) e->strategy = 3;
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     e->T.spill_slots = 1024;
@@ -323,7 +325,7 @@ int32_t qe_fused_grid_blocks(qe_engine_t* e) { return e->last_grid; }
 int32_t qe_fused_form(qe_engine_t* e) { return e->current; }
 int qe_set_fused_form(qe_engine_t* e, int32_t form) {
     std::lock_guard<std::mutex> lk(e->mu);
-    if (form < 0 || form > 3) return fail(QE_ERR_ARG, "form must be 0 (writer lists), 1 (per-step sort), 2 (pick between those two by measurement) or 3 (target pipeline)");
+    if (form < 0 || form == 4 || form > 5) return fail(QE_ERR_ARG, "form must be 0 (writer lists), 1 (per-step sort), 2 (pick between those two by measurement), 3 (target pipeline) or 5 (one-pass form)");
     e->strategy = form;
     return QE_OK;
 }
@@ -830,9 +832,10 @@ constexpr int kProbeEvery = 12;
 static int pick_form(qe_engine* e, const FusedArgs& F, bool* time_it) {
     *time_it = false;
     // small batches: one CTA, no grid barrier (qe_small.cuh); QE_FORM / qe_set_fused_form(0..2) still pin the grid-wide forms
-    if (F.n <= kSmallMaxAgents && e->A <= 32 && e->S < (1ll << 26) && !F.accumulate && e->strategy == 3 && !getenv("QE_NO_SMALL")) return 4;
+    if (F.n <= kSmallMaxAgents && e->A <= 32 && e->S < (1ll << 26) && !F.accumulate && (e->strategy == 3 || e->strategy == 5) && !getenv("QE_NO_SMALL")) return 4;
     if (e->state_base != 0 || e->A > 32 || !e->X.seg) return 0;
     if (F.accumulate || F.evaluate) return 0;  // the plain-atomics update and the evaluation loop live in fused_kernel
+    if (e->strategy == 5) return (e->S < (1ll << 30) && F.n <= (1 << 24)) ? 5 : 1;  // writer records keep the agent in 24 bits
     if (e->strategy == 3) return e->S < (1ll << 30) ? 3 : 1;  // the pipeline's records keep the state in 30 bits
     if (e->strategy == 0 || e->strategy == 1) return e->strategy;
     if (e->timed_kind >= 0) {  // collect the launch timed last
@@ -878,7 +881,49 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
         blocks = 1;
         void* args[] = {&T, &F};
         CK(cudaLaunchKernel((void*)fused_small_kernel<ENV, LPR>, dim3(1), dim3(kSmallMaxAgents), args, 0, st));
+    } else if (form == 5) {
+        const size_t smem = flow_smem_bytes(LPR);
+        CK(cudaFuncSetAttribute(fused_flow_kernel<ENV, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_flow_kernel<ENV, LPR>, 256, smem));
+        if (per_sm < 1) return fail(QE_ERR_CUDA, "the one-pass kernel cannot be made resident");
+        {
+            const long long want = ((long long)F.n + 255) / 256, maxb = (long long)per_sm * e->sms;
+            blocks = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
+        }
+        if (blocks > 32 * kScanPerLane) blocks = 32 * kScanPerLane;
+        int rc = ensure_pipe(e, blocks);
+        if (rc) return rc;
+        if (e->pipe_kind != 5 && (e->pipe_sorted_n > 0 || e->pipe_valid)) {  // bounds left by the other pipelined form: start from all-empty
+            CK(cudaMemsetAsync(e->P.seg, 0, sizeof(uint2) * (size_t)e->S, st));
+            e->pipe_valid = false;
+            e->pipe_sorted_n = 0;
+        }
+        FlowScratch X{};
+        X.rec = reinterpret_cast<uint64_t*>(e->P.rec); X.seg = e->P.seg; X.pos = e->P.pos; X.kv[0] = e->P.kv[0]; X.kv[1] = e->P.kv[1];
+        X.ghist = e->P.ghist; X.rowtot = e->P.rowtot; X.ctr = e->P.ctr;
+        {
+            int bits = 1;
+            while (bits < 31 && (1ll << bits) < e->S) ++bits;
+            X.msd_shift = bits > kRadixBits ? bits - kRadixBits : 0;
+            X.local_passes = (X.msd_shift + kRadixBits - 1) / kRadixBits;
+        }
+        X.sorted_valid = (e->pipe_valid && e->pipe_states == F.st_a && e->pipe_n == F.n && !getenv("QE_PIPE_RESORT")) ? 1 : 0;
+        X.old_n = e->pipe_sorted_n;
+        CK(cudaMemsetAsync(e->P.ctr, 0, 64 * sizeof(unsigned int), st));
+        void* args[] = {&T, &F, &X};
+        CK(cudaLaunchCooperativeKernel((void*)fused_flow_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, smem, st));
+        e->pipe_valid = true;
+        e->pipe_states = F.st_a;
+        e->pipe_n = F.n;
+        e->pipe_sorted_n = F.n;
+        e->pipe_kind = 5;
     } else if (form == 3) {
+        if (e->pipe_kind != 3 && (e->pipe_sorted_n > 0 || e->pipe_valid)) {  // bounds left by the one-pass form
+            CK(cudaMemsetAsync(e->P.seg, 0, sizeof(uint2) * (size_t)e->S, st));
+            e->pipe_valid = false;
+            e->pipe_sorted_n = 0;
+        }
         const size_t smem = pipe_smem_bytes(LPR);
         CK(cudaFuncSetAttribute(fused_pipe_kernel<ENV, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -902,6 +947,7 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
         e->pipe_states = F.st_a;
         e->pipe_n = F.n;
         e->pipe_sorted_n = F.n;
+        e->pipe_kind = 3;
     } else if (form == 1) {
         if (!F.evaluate) e->pipe_valid = false;
         int rc = coop_blocks(e, fused_sorted_kernel<ENV, LPR>, (long long)F.n, &blocks);

@@ -1,0 +1,641 @@
+// qe_flow.cuh -- the one-pass form of the fused loop (round 2): select, environment step and the exact sequential TD
+// update of an agent happen back to back in ONE in-order pass over the agents, four grid barriers per vector step.
+//
+// It keeps the two ideas of the target pipeline (qe_pipe.cuh): what an agent contributes to the table is its TARGET
+// t_i = r_i + gamma * max_a Q_i[s'_i, a] (QLO:760-768), and anybody who knows the targets of the earlier writers of a
+// row (a prefix of the row's segment in a stable sort of the agents by state) can replay the row from its value at
+// the start of the step; and chunks of 32 agents are claimed in increasing order, so a dependency always points to an
+// agent that was claimed earlier.  What changes:
+//
+//   * select + environment step (round 2's phase A) and the target pipeline (phase T) are one phase.  The table is only
+//     written by the commit, so "select" of agent i may run while the targets of agents j < i are still being resolved:
+//     the row gathers of select (throughput) and the publish -> poll hops of the targets (latency) overlap, the
+//     per-agent hand-over array between the phases (16 B per agent each way) and one grid barrier are gone.  A warp
+//     claims a chunk, selects and steps its 32 agents, fetches their bootstrap rows into shared memory and polls the
+//     writer records of s'_i until every lane has published its target; then it claims the next chunk.
+//   * a writer record is one 64-bit word {agent | action << 24 | flags, value}: the sort of the previous step leaves
+//     {agent, 0} at every position, the agent's warp overwrites it once with FINAL (value = target; terminated agents
+//     at once, QLO:760-766) and before that, for a self loop (s' = s), with SELF (value = reward: the reader derives
+//     the target from the row it is replaying, which IS the row the writer bootstraps from).  One 8-byte store, one
+//     256-bit load per four records: no separate "pending" pass, no barrier between filing and reading.
+//   * the order of the next states is an MSD bucket sort instead of LSD passes over the grid: the top (up to) 10 bits
+//     are a stable partition over all CTAs (digit counts per CTA taken in the tail of the in-order pass, column scan
+//     beside the commit, scatter), the remaining bits are sorted bucket by bucket inside one CTA with block barriers
+//     only; the same CTA then writes position, segment bounds and the initial writer records of its bucket.
+//
+// Per vector step:   [ select + step + targets | digit counts ]  B  [ column scan, commit ]  B  [ scatter ]  B
+//                    [ bucket sorts, positions, bounds, records ]  B
+// Same floating-point operations in the same order as the reference: bit-identical to the oracle and to the other forms.
+// Requires the legal-action mask to be a function of the state (true for the device environments).
+#pragma once
+#include "qe_pipe.cuh"
+
+namespace qe {
+
+constexpr uint32_t kRecSelf = 1u << 29;   // value = reward of a writer whose next state is its own row
+constexpr uint32_t kRecFinal = 1u << 30;  // value = target
+constexpr uint32_t kRecAgent = 0xFFFFFFu;
+
+struct FlowScratch {
+    uint64_t* rec;        // [cap + 8] writer records by sorted position (see above)
+    uint2* seg;           // [S] per state {segment start, segment end} ({0, 0}: nobody stands on the state)
+    int32_t* pos;         // [cap] agent -> sorted position
+    int2* kv[2];          // [cap] {state, agent} by position; the finished order is always in kv[0]
+    int* ghist;           // [kRadix][blocks] bucket counts per block, scanned in place
+    int* rowtot;          // [kRadix] bucket totals
+    unsigned int* ctr;    // [64] 0: chunk claims; 1: chunks selected + stepped; 2: commit tile claims; 4: abort; 6: order invalid
+    int msd_shift;        // bucket = state >> msd_shift (< kRadix)
+    int local_passes;     // LSD passes (kRadixBits each) over the low msd_shift bits inside a bucket
+    int sorted_valid;     // pos / seg / kv[0] / rec describe the states this launch starts from (to be checked)
+    int old_n;            // agents of the order kv[0] and seg[] still describe (0: none, seg[] is all-empty)
+};
+
+__device__ __forceinline__ void st_relaxed_rec(uint64_t* p, uint32_t x, uint32_t y) {
+    st_relaxed_u64(p, (uint64_t)x | ((uint64_t)y << 32));
+}
+
+// static split of [0, n) in whole tiles of 32: block b of nb, warp w of WARPS -> [lo, hi) (sizes differ by at most one tile)
+template <int WARPS>
+__device__ __forceinline__ void flow_part(int n, int b, int nb, int w, int& lo, int& hi) {
+    const int tiles = (n + 31) >> 5;
+    const int per = tiles / nb, rem = tiles % nb;
+    const int t0 = b * per + min(b, rem), bt = per + (b < rem ? 1 : 0);
+    const int pw = bt / WARPS, rw = bt % WARPS;
+    const int w0 = t0 + w * pw + min(w, rw), w1 = w0 + pw + (w < rw ? 1 : 0);
+    lo = min(w0 * 32, n);
+    hi = min(w1 * 32, n);
+}
+
+// ---- bucket counts of this block's part of states[] -> whist (kept for the scatter) and ghist[bucket][block]
+template <int WARPS>
+__device__ __forceinline__ void flow_hist(int (*whist)[kRadix], const int32_t* states, int n, const FlowScratch& X) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x, nb = gridDim.x;
+    int lo, hi;
+    flow_part<WARPS>(n, b, nb, warp, lo, hi);
+    for (int d = lane; d < kRadix; d += 32) whist[warp][d] = 0;
+    __syncwarp();
+    const int sh = X.msd_shift;
+    for (int base = lo; base < hi; base += 256) {  // eight loads in flight per lane
+        int32_t kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kk[u] = base + 32 * u + lane < hi ? __ldcg(states + base + 32 * u + lane) : 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + 32 * u + lane < hi) atomicAdd(&whist[warp][(uint32_t)kk[u] >> sh], 1);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) t += whist[w][d];
+        X.ghist[(size_t)d * nb + b] = t;
+    }
+}
+
+// ---- exclusive scan of every bucket's row of block counts (one warp per bucket), bucket totals
+template <int WARPS>
+__device__ __forceinline__ void flow_scan(const FlowScratch& X) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = gridDim.x;
+    const int gw = blockIdx.x * WARPS + warp, nw = nb * WARPS;
+    const int per = (nb + 31) / 32;
+    for (int d = gw; d < kRadix; d += nw) {
+        int* row = X.ghist + (size_t)d * nb;
+        int v[kScanPerLane];
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < kScanPerLane; ++j) {
+            const int x = lane * per + j;
+            v[j] = (j < per && x < nb) ? __ldcg(row + x) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < kScanPerLane; ++j) sum += v[j];
+        const int incl = warp_incl_scan(sum);
+        int run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < kScanPerLane; ++j) {
+            const int x = lane * per + j;
+            if (j < per && x < nb) row[x] = run;
+            run += v[j];
+        }
+        if (lane == 31) X.rowtot[d] = incl;
+    }
+}
+
+// ---- stable scatter of this block's part into the buckets; s_base[0 .. kRadix] = bucket starts (kept for the bucket sorts)
+template <int WARPS>
+__device__ __forceinline__ void flow_scatter(int (*whist)[kRadix], int* s_base, int* s_wsum, const int32_t* states, int n, int2* out,
+                                             const FlowScratch& X) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x, nb = gridDim.x;
+    static_assert(kRadix == 4 * 256, "four buckets per thread");
+    {
+        const int4 v4 = __ldcg(reinterpret_cast<const int4*>(X.rowtot) + threadIdx.x);
+        const int v[4] = {v4.x, v4.y, v4.z, v4.w};
+        const int sum = v4.x + v4.y + v4.z + v4.w;
+        const int incl = warp_incl_scan(sum);
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) before += (w < warp) ? s_wsum[w] : 0;
+        int run = before + incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s_base[threadIdx.x * 4 + j] = run; run += v[j]; }
+        if (threadIdx.x == 255) s_base[kRadix] = run;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+        int run = s_base[d] + __ldcg(X.ghist + (size_t)d * nb + b);
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const int c = whist[w][d];
+            whist[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    int lo, hi;
+    flow_part<WARPS>(n, b, nb, warp, lo, hi);
+    const int sh = X.msd_shift;
+    for (int base = lo; base < hi; base += 256) {
+        int32_t kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kk[u] = base + 32 * u + lane < hi ? __ldcg(states + base + 32 * u + lane) : 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int x = base + 32 * u + lane;
+            if (base + 32 * u >= hi) break;  // (uniform)
+            const bool act = x < hi;
+            const uint32_t d = (uint32_t)kk[u] >> sh;
+            const uint32_t peers = digit_peers(d, act);
+            if (act) out[whist[warp][d] + __popc(peers & ((1u << lane) - 1u))] = make_int2(kk[u], x);
+            __syncwarp();
+            if (act && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
+            __syncwarp();
+        }
+    }
+}
+
+// ---- one stable counting pass over [lo, hi) of src -> dst by the digit (key >> shift) & (2^bits - 1), whole block
+template <int WARPS>
+__device__ __forceinline__ void flow_local_pass(int (*whist)[kRadix], int* s_wsum, const int2* src, int2* dst, int lo, int hi, int shift,
+                                                int bits) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nd = 1 << bits;
+    const uint32_t dm = (uint32_t)nd - 1u;
+    const int tiles = (hi - lo + 31) >> 5;
+    const int pw = tiles / WARPS, rw = tiles % WARPS;
+    const int w0 = warp * pw + min(warp, rw), w1 = w0 + pw + (warp < rw ? 1 : 0);
+    const int wlo = min(lo + w0 * 32, hi), whi = min(lo + w1 * 32, hi);
+    for (int d = lane; d < nd; d += 32) whist[warp][d] = 0;
+    __syncwarp();
+    for (int base = wlo; base < whi; base += 32) {
+        const int x = base + lane;
+        if (x < whi) atomicAdd(&whist[warp][((uint32_t)__ldcg(&src[x].x) >> shift) & dm], 1);
+    }
+    __syncthreads();
+    {   // digit totals, exclusive scan over the digits (thread t owns `per` consecutive digits), first free position per (digit, warp)
+        const int per = nd >= 256 ? nd / 256 : 1;
+        int v[4] = {0, 0, 0, 0};
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = threadIdx.x * per + j;
+            if (j < per && d < nd) {
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) v[j] += whist[w][d];
+            }
+            sum += v[j];
+        }
+        const int incl = warp_incl_scan(sum);
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) before += (w < warp) ? s_wsum[w] : 0;
+        int run = lo + before + incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = threadIdx.x * per + j;
+            if (j < per && d < nd) {
+                int r2 = run;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) {
+                    const int c = whist[w][d];
+                    whist[w][d] = r2;
+                    r2 += c;
+                }
+                run += v[j];
+            }
+        }
+    }
+    __syncthreads();
+    for (int base = wlo; base < whi; base += 32) {
+        const int x = base + lane;
+        const bool act = x < whi;
+        int2 e = make_int2(0, 0);
+        if (act) e = __ldcg(src + x);
+        const uint32_t d = ((uint32_t)e.x >> shift) & dm;
+        const uint32_t peers = digit_peers(d, act);
+        if (act) dst[whist[warp][d] + __popc(peers & ((1u << lane) - 1u))] = e;
+        __syncwarp();
+        if (act && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// ---- the buckets of this block: sort by the low bits, then positions, segment bounds and fresh writer records
+template <int WARPS>
+__device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], const int* s_base, int* s_wsum, const FlowScratch& X) {
+    const int L = X.local_passes;
+    for (int d = blockIdx.x; d < kRadix; d += gridDim.x) {
+        const int lo = s_base[d], hi = s_base[d + 1];
+        if (hi <= lo) continue;  // (uniform)
+        int src = L & 1;
+        for (int ps = 0; ps < L; ++ps) {
+            const int shift = ps * kRadixBits;
+            flow_local_pass<WARPS>(whist, s_wsum, X.kv[src], X.kv[src ^ 1], lo, hi, shift, min(kRadixBits, X.msd_shift - shift));
+            src ^= 1;
+        }
+        const int2* fin = X.kv[0];
+        for (int q = lo + threadIdx.x; q < hi; q += blockDim.x) {
+            const int2 e = __ldcg(fin + q);
+            const int32_t prev = q > lo ? __ldcg(&fin[q - 1].x) : -1, next = q + 1 < hi ? __ldcg(&fin[q + 1].x) : -1;
+            X.pos[e.y] = q;
+            X.rec[q] = (uint64_t)(uint32_t)e.y;
+            if (prev != e.x) X.seg[e.x].x = (uint32_t)q;
+            if (next != e.x) X.seg[e.x].y = (uint32_t)(q + 1);
+        }
+    }
+}
+
+__host__ __device__ constexpr int flow_row_words(int lpr) { return 8 * lpr + 4; }  // one replayed row per thread, 16-byte aligned, conflict-free
+__host__ __device__ constexpr size_t flow_smem_bytes(int lpr) {
+    return sizeof(int) * ((size_t)8 * kRadix + kRadix + 8) + sizeof(float) * (size_t)flow_row_words(lpr) * 256;
+}
+#ifndef QE_FLOW_MIN_BLOCKS
+#define QE_FLOW_MIN_BLOCKS 3
+#endif
+template <int ENV, int LPR>
+__global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Table T, FusedArgs F, FlowScratch X) {
+    cg::grid_group grid = cg::this_grid();
+    constexpr int WARPS = 8;
+    constexpr int RS = flow_row_words(LPR);
+    __shared__ double s_sum[8];
+    __shared__ unsigned int s_cnt[8];
+    __shared__ int s_wsum[WARPS];
+    extern __shared__ __align__(16) unsigned char s_raw[];  // flow_smem_bytes(LPR)
+    int (*s_whist)[kRadix] = reinterpret_cast<int (*)[kRadix]>(s_raw);            // [8][kRadix] per-warp digit counters
+    int* s_base = reinterpret_cast<int*>(s_raw) + WARPS * kRadix;                 // [kRadix + 1] bucket starts
+    float* s_rows = reinterpret_cast<float*>(s_base + kRadix + 8);                // in-order pass: [256][RS]; commit: [8*LPR][256] + [256]
+    float* s_row = s_rows;
+    uint32_t* s_touch = reinterpret_cast<uint32_t*>(s_rows) + 8 * LPR * 256;
+    static_assert((8 * LPR + 1) * 256 <= RS * 256, "the commit's columns fit in the rows region");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    const uint32_t full = T.A >= 32 ? 0xFFFFFFFFu : ((1u << T.A) - 1u);
+    const int n = F.n;
+    const int ntiles = (n + 31) >> 5;
+    const bool clk = F.phase_ns != nullptr && tid == 0;
+    const int wbase = threadIdx.x & ~31;
+    uint64_t* rec = X.rec;
+    const int2* sorted = X.kv[0];
+    if (clk) F.phase_ns[0] = global_ns();
+
+    // ---------------- the order of the states this launch starts from: left behind by the previous launch (checked), else made now
+    {
+        bool bad = !X.sorted_valid;
+        if (!bad)
+            for (int i = tid; i < n; i += nthreads) {
+                const uint32_t q = (uint32_t)__ldcg(X.pos + i);
+                if (q >= (uint32_t)n) { bad = true; continue; }
+                const int2 e = __ldcg(sorted + q);
+                bad |= e.y != i || e.x != __ldcg(F.st_a + i) || __ldcg(rec + q) != (uint64_t)(uint32_t)i;
+            }
+        if (__syncthreads_or(bad) && threadIdx.x == 0) atomicExch(X.ctr + 6, 1u);
+        grid.sync();
+        if (ld_relaxed_u32(X.ctr + 6) != 0u) {  // (the same answer in every block)
+            for (int q = tid; q < X.old_n; q += nthreads) {  // the bounds of the order kv[0] still describes
+                const int32_t kq = __ldcg(&sorted[q].x);
+                if (q == 0 || __ldcg(&sorted[q - 1].x) != kq) X.seg[kq] = make_uint2(0u, 0u);
+            }
+            flow_hist<WARPS>(s_whist, F.st_a, n, X);
+            grid.sync();
+            flow_scan<WARPS>(X);
+            grid.sync();
+            flow_scatter<WARPS>(s_whist, s_base, s_wsum, F.st_a, n, X.kv[X.local_passes & 1], X);
+            grid.sync();
+            flow_buckets<WARPS>(s_whist, s_base, s_wsum, X);
+            grid.sync();
+        }
+    }
+
+    for (int k = 0; k < F.steps; ++k) {
+        int32_t* cur = (k & 1) ? F.st_b : F.st_a;
+        int32_t* nxt = (k & 1) ? F.st_a : F.st_b;
+        Uniforms U{F.uniforms ? F.uniforms + (size_t)k * n * F.slots : nullptr, F.slots, F.stream_seed, F.t0 + (uint32_t)k, F.agent0,
+                   F.env_stream_seed, F.env_t0 + (uint32_t)k};
+        const uint64_t thresh = F.eps_thresh[k];
+        const float lr = F.lr[k];
+        double loc_sum = 0.0;
+        unsigned int loc_cnt = 0;
+
+        // ---------------- the in-order pass: select + environment step + target, chunk by chunk
+        {
+            unsigned int* claim = X.ctr;
+            float* myrow = s_rows + threadIdx.x * RS;
+            auto claim_chunk = [&]() {
+                int c = 0;
+                if (lane == 0) c = (int)atomicAdd(claim, 1u);
+                return __shfl_sync(kFull, c, 0) * 32;
+            };
+            auto row_max = [&]() {
+                float m = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 2 * LPR; ++c) {
+                    const float4 v = reinterpret_cast<const float4*>(myrow)[c];
+                    m = fmaxf(fmaxf(fmaxf(fmaxf(m, v.x), v.y), v.z), v.w);
+                }
+                return m;
+            };
+            int cb = claim_chunk();
+            int s_nx = 0, pos_nx = 0;
+            if (cb + lane < n) { s_nx = cur[cb + lane]; pos_nx = X.pos[cb + lane]; }
+            int cbn = claim_chunk();
+            const uint64_t t_start = global_ns();
+            bool aborted = false;
+            while (cb < n && !aborted) {
+                const int i = cb + lane;
+                const bool active = i < n;
+                const int s = s_nx, mypos = pos_nx;
+                if (cbn + lane < n) { s_nx = cur[cbn + lane]; pos_nx = X.pos[cbn + lane]; }
+                uint32_t ew = 0u, valid = 0u, bits1 = 0u;
+                bool explore = false;
+                if (active) {
+                    if (ENV != 0) ew = F.envw[i];
+                    valid = F.use_masks ? env_mask<ENV>(s, ew, T.A, F.env_seed) : full;
+                    explore = (uint64_t)U.draw(i, 0) < thresh;
+                    bits1 = U.draw(i, 1);
+                }
+                int32_t s2 = s;
+                float r = 0.0f;
+                bool term = false;
+                int a;
+                {
+                    RowGather<LPR> rows;
+                    rows.issue(T, s, active);
+                    float mx;
+                    uint32_t tie;
+                    rows.row_max_tie(valid, mx, tie);
+                    a = pick_action(T.A, valid, tie, explore, F.empty_all != 0, bits1);
+                }
+                if (active && a < 0) { atomicOr(T.err, kErrEmpty); a = 0; }
+                a = max(a, 0);
+                if (active) {
+                    if (ENV == 0) mdp_step(s2, a, (uint32_t)F.S, T.A, F.env_seed, F.term_thresh, U.draw(i, 2), U.draw(i, 3), r, term);
+                    else if (ENV == 1) {
+                        if (!ttt_step(ew, a, U.draw(i, 2), U.draw(i, 3), U.draw(i, 4), r, term)) atomicOr(T.err, kErrInvalidMove);
+                        s2 = ttt_state(ew & 0x3FFFFu);
+                    } else {
+                        r = (float)a;
+                        ew += 1u;
+                        term = ew >= F.episode_len;
+                        if (term) ew = 0u;
+                        s2 = 0;
+                    }
+                    nxt[i] = s2;
+                    if (ENV != 0) F.envw[i] = ew;
+                    float acc = F.ep_ret[i] + r;
+                    float fin = __int_as_float(0x7FC00000);
+                    if (term) { fin = acc; loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
+                    F.ep_ret[i] = acc;
+                    const size_t o = (size_t)k * n + i;
+                    if (F.trace_actions) F.trace_actions[o] = a;
+                    if (F.trace_rewards) F.trace_rewards[o] = r;
+                    if (F.trace_term) F.trace_term[o] = term;
+                    if (F.trace_next) F.trace_next[o] = s2;
+                    if (F.trace_epret) F.trace_epret[o] = fin;
+                }
+                __syncwarp();
+                if (lane == 0) { __threadfence(); atomicAdd(X.ctr + 1, 1u); }  // this chunk's next states are in place (bucket counts wait for all of them)
+
+                // ---- targets.  A terminated agent bootstraps from nothing (QLO:760-766): final at once; a self loop says so
+                const bool need = active && !term;
+                const uint32_t head = (uint32_t)i | ((uint32_t)a << 24);
+                uint32_t m2 = 0u;
+                uint2 sg = make_uint2(0u, 0u);
+                if (active && term) st_relaxed_rec(rec + mypos, head | kRecFinal, __float_as_uint(td_target_s(r, 0.0f, F.gamma)));
+                if (need) {
+                    if (s2 == s) st_relaxed_rec(rec + mypos, head | kRecSelf, __float_as_uint(r));
+                    m2 = F.use_masks ? state_mask<ENV>(s2, T.A, F.env_seed, full) : full;
+                    if (m2 == 0u) atomicOr(T.err, kErrEmpty);  // np.max of an empty selection (QLO:764)
+                    sg = __ldcg(X.seg + s2);
+                }
+                {   // bootstrap rows, transposed gather: the LPR lanes of a group deposit one agent's row (illegal cells at -inf) in its owner's slot
+                    RowGather<LPR> rows;
+                    rows.issue(T, s2, need);
+                    constexpr int G = 32 / LPR;
+                    const int l = lane & (LPR - 1), g = lane / LPR;
+#pragma unroll
+                    for (int q = 0; q < LPR; ++q) {
+                        const int owner = q * G + g;
+                        const uint32_t mo = (__shfl_sync(kFull, m2, owner) >> (8 * l)) & 0xFFu;
+                        float w8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w8[j] = ((mo >> j) & 1u) ? rows.v[q].v[j] : -INFINITY;
+                        float4* dst = reinterpret_cast<float4*>(s_rows + (wbase + owner) * RS + 8 * l);
+                        dst[0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+                        dst[1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                    }
+                }
+                __syncwarp();
+                uint32_t p = sg.x, pe = sg.y;
+                if (!(p < pe && pe <= (uint32_t)n)) p = pe = 0u;
+                bool busy = need;
+                for (uint32_t spins = 0; __any_sync(kFull, busy); ++spins) {
+                    if (busy) {
+                        bool fin = p >= pe;
+                        if (!fin) {
+                            const uint32_t pa = p & ~3u;
+                            const U8 ea = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa));
+                            U8 eb;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) eb.w[j] = 0xFFFFFFFFu;  // (agent ids beyond every i: the scan stops there)
+                            if (pa + 4 < pe) eb = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa + 4));
+                            bool stop = false;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint32_t ex = j < 4 ? ea.w[2 * j] : eb.w[2 * (j - 4)], ey = j < 4 ? ea.w[2 * j + 1] : eb.w[2 * (j - 4) + 1];
+                                if (!stop && !fin && pa + j >= p) {
+                                    if (pa + j >= pe || (int)(ex & kRecAgent) >= i) {
+                                        fin = true;  // the segment ends here, or the writers from here on come after i
+                                    } else if (ex & (kRecFinal | kRecSelf)) {
+                                        const float tg = (ex & kRecFinal) ? __uint_as_float(ey) : td_target_s(__uint_as_float(ey), row_max(), F.gamma);
+                                        const uint32_t a2 = (ex >> 24) & 31u;
+                                        if ((m2 >> a2) & 1u) {  // an illegal cell stays at -inf: it cannot be the masked max
+                                            float* cell = myrow + a2;
+                                            *cell = td_from_target_s(*cell, tg, lr);
+                                        }
+                                        ++p;
+                                    } else {
+                                        stop = true;  // an earlier writer that has not published yet
+                                    }
+                                }
+                            }
+                            if (!stop && p >= pe) fin = true;
+                        }
+                        if (fin) {
+                            st_relaxed_rec(rec + mypos, head | kRecFinal, __float_as_uint(td_target_s(r, row_max(), F.gamma)));
+                            busy = false;
+                        }
+                    }
+                    if ((spins & 255u) == 255u) {  // (all lanes take the same way out)
+                        if (__any_sync(kFull, ld_relaxed_u32(X.ctr + 4) != 0u || global_ns() - t_start > kPipeTimeoutNs)) {
+                            atomicExch(X.ctr + 4, 1u);
+                            atomicOr(T.err, kErrTimeout);
+                            aborted = true;
+                            break;
+                        }
+                    }
+                }
+                cb = cbn;
+                cbn = claim_chunk();
+            }
+            // ---- tail: once every chunk has been selected and stepped, the bucket counts of this block's part of the next states
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (uint32_t spins = 0; ld_relaxed_u32(X.ctr + 1) < (unsigned int)ntiles; ++spins) {
+                    __nanosleep(64);
+                    if ((spins & 255u) == 255u && (ld_relaxed_u32(X.ctr + 4) != 0u || global_ns() - t_start > kPipeTimeoutNs)) {
+                        atomicExch(X.ctr + 4, 1u);
+                        atomicOr(T.err, kErrTimeout);
+                        break;
+                    }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            flow_hist<WARPS>(s_whist, nxt, n, X);  // (after a timeout the counts are garbage and so is everything else: the error flag says so)
+        }
+        if (F.ep_count) {
+            for (int d = 16; d > 0; d >>= 1) {
+                loc_sum += __shfl_xor_sync(kFull, loc_sum, d);
+                loc_cnt += __shfl_xor_sync(kFull, loc_cnt, d);
+            }
+            if (lane == 0) { s_sum[warp] = loc_sum; s_cnt[warp] = loc_cnt; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double bs = 0.0;
+                unsigned int bc = 0;
+                for (int w = 0; w < WARPS; ++w) { bs += s_sum[w]; bc += s_cnt[w]; }
+                if (bc) { atomicAdd(F.ep_sum, bs); atomicAdd(F.ep_count, (unsigned long long)bc); }
+            }
+        }
+        grid.sync();
+        if (clk && k < 10) F.phase_ns[1 + 3 * k] = global_ns();
+
+        // ---------------- column scan of the bucket counts (the first kRadix warps) and the commit: one pass over the sorted
+        // records, tiles claimed dynamically; a segment's row lives in the shared-memory column of its head lane, the
+        // members take turns in position (= agent) order; what extends beyond the tile is replayed by the whole warp, one
+        // lane per action.  The bounds of the segment are cleared on the way (the bucket sorts write the next ones).
+        flow_scan<WARPS>(X);
+        for (;;) {
+            int tile = 0;
+            if (lane == 0) tile = (int)atomicAdd(X.ctr + 2, 2u);
+            tile = __shfl_sync(kFull, tile, 0);
+            if (tile >= ntiles) break;
+            for (const int tend = min(tile + 2, ntiles); tile < tend; ++tile) {
+                const int p = tile * 32 + lane;
+                const bool act = p < n;
+                uint64_t e = 0ull;
+                uint32_t st = 0xFFFFFFFFu;  // state of this position
+                if (act) { e = __ldcg(rec + p); st = (uint32_t)__ldcg(&sorted[p].x); }
+                const uint32_t ex = (uint32_t)e, ey = (uint32_t)(e >> 32);
+                uint32_t prev = __shfl_up_sync(kFull, st, 1);
+                if (lane == 0) prev = p > 0 ? (uint32_t)__ldcg(&sorted[p - 1].x) : 0xFFFFFFFFu;
+                const bool head = act && (p == 0 || prev != st);
+                const uint32_t hb = __ballot_sync(kFull, head);
+                const uint32_t below = hb & (0xFFFFFFFFu >> (31 - lane));
+                const int hl = below ? 31 - __clz(below) : -1;  // head lane of this lane's segment; -1: the segment began in an earlier tile
+                if (act && !(ex & kRecFinal)) atomicOr(T.err, kErrTimeout);  // cannot happen: the in-order pass published every target
+                if (head) {
+                    const float* row = T.q + (size_t)st * T.ld;
+#pragma unroll
+                    for (int c = 0; c < LPR; ++c) {
+                        const F8 v8 = ld_row8(row + 8 * c);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s_row[(8 * c + j) * 256 + threadIdx.x] = v8.v[j];
+                    }
+                    s_touch[threadIdx.x] = 0u;
+                    X.seg[st] = make_uint2(0u, 0u);
+                }
+                __syncwarp();
+                const int off = (act && hl >= 0) ? lane - hl : -1;
+                const int maxoff = (int)__reduce_max_sync(kFull, off);
+                for (int it = 0; it <= maxoff; ++it) {
+                    if (off == it) {
+                        const int c = wbase + hl;
+                        const uint32_t a = (ex >> 24) & 31u;
+                        float* cell = s_row + a * 256 + c;
+                        *cell = td_from_target_s(*cell, __uint_as_float(ey), lr);
+                        s_touch[c] |= 1u << a;
+                    }
+                    __syncwarp();
+                }
+                // the tile's last segment may go on in the following tiles
+                const int hl31 = __shfl_sync(kFull, hl, 31);
+                const uint32_t st31 = __shfl_sync(kFull, st, 31);
+                if (hl31 >= 0 && tile * 32 + 32 < n) {
+                    const int c = wbase + hl31;
+                    float v = lane < 8 * LPR ? s_row[lane * 256 + c] : 0.0f;
+                    bool touched = false;
+                    for (int q = tile * 32 + 32; q < n; q += 32) {
+                        uint64_t e2 = 0ull;
+                        uint32_t k2 = 0xFFFFFFFFu;
+                        if (q + lane < n) { e2 = __ldcg(rec + q + lane); k2 = (uint32_t)__ldcg(&sorted[q + lane].x); }
+                        const uint32_t diff = __ballot_sync(kFull, k2 != st31);
+                        const int len = diff ? __ffs(diff) - 1 : 32;
+                        for (int j = 0; j < len; ++j) {
+                            const uint32_t xa = (__shfl_sync(kFull, (uint32_t)e2, j) >> 24) & 31u;
+                            const float tg = __uint_as_float(__shfl_sync(kFull, (uint32_t)(e2 >> 32), j));
+                            if ((uint32_t)lane == xa) { v = td_from_target_s(v, tg, lr); touched = true; }
+                        }
+                        if (len < 32) break;
+                    }
+                    const uint32_t tb = __ballot_sync(kFull, touched);
+                    if (lane < 8 * LPR) s_row[lane * 256 + c] = v;
+                    if (lane == 0) s_touch[c] |= tb;
+                }
+                __syncwarp();
+                if (head) {
+                    float* row = T.q + (size_t)st * T.ld;
+                    for (uint32_t bm = s_touch[threadIdx.x]; bm; bm &= bm - 1u) {
+                        const int a = __ffs(bm) - 1;
+                        row[a] = s_row[a * 256 + threadIdx.x];
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        grid.sync();
+        if (clk && k < 10) F.phase_ns[2 + 3 * k] = global_ns();
+
+        // ---------------- the next step's order: stable scatter into the buckets, then every bucket inside one block
+        if (tid == 0) { X.ctr[0] = 0u; X.ctr[1] = 0u; X.ctr[2] = 0u; }  // (idle since the last barrier; next used after two more)
+        flow_scatter<WARPS>(s_whist, s_base, s_wsum, nxt, n, X.kv[X.local_passes & 1], X);
+        grid.sync();
+        if (clk && k < 10) F.phase_ns[32 + k] = global_ns();
+        flow_buckets<WARPS>(s_whist, s_base, s_wsum, X);
+        grid.sync();
+        if (clk && k < 10) F.phase_ns[3 + 3 * k] = global_ns();
+    }
+    if (F.steps & 1) {
+        for (int i = tid; i < n; i += nthreads) F.st_a[i] = F.st_b[i];
+    }
+}
+
+}  // namespace qe

@@ -66,6 +66,9 @@ if m >= 4:
 if lib.qe_fused_form(h) == 3 and m >= 4:
     print("  pipelined form: A = select + env step, B1 = target pipeline, B2 = commit + sort of the next states; commit us:",
           " ".join(f"{(buf[32 + k] - ts[2 + 3 * k]) / 1e3:.1f}" for k in range((m - 1) // 3)), "| sort us:", " ".join(f"{(ts[3 + 3 * k] - buf[32 + k]) / 1e3:.1f}" for k in range((m - 1) // 3)))
+if lib.qe_fused_form(h) == 5 and m >= 4:
+    print("  one-pass form: A = select + step + targets (+ bucket counts), B1 = column scan + commit, B2 = sort of the next states; scatter us:",
+          " ".join(f"{(buf[32 + k] - ts[2 + 3 * k]) / 1e3:.1f}" for k in range((m - 1) // 3)), "| bucket sorts us:", " ".join(f"{(ts[3 + 3 * k] - buf[32 + k]) / 1e3:.1f}" for k in range((m - 1) // 3)))
 cnt = (C.c_uint64 * 56)()
 if lib.qe_fused_form(h) == 3:
     if lib.qe_debug_counters(h, cnt, 2) == 0 and cnt[0]:

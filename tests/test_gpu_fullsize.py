@@ -153,10 +153,10 @@ def test_config3_chunking_and_determinism(capi):
             x.close()
 
 
-@pytest.mark.parametrize("form", ["0", "1", "3"])
+@pytest.mark.parametrize("form", ["0", "1", "3", "5"])
 @pytest.mark.parametrize("S,A,N,steps", [(2000, 16, 50_000, 24), (97, 5, 4096, 16), (300_000, 8, 200_000, 10), (3, 20, 1000, 6), (70_000, 32, 33, 40)])
 def test_all_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form, S, A, N, steps):
-    """QE_FORM pins the form of the TD update (0 = writer lists, 1 = per-step sort, 3 = target pipeline); all must
+    """QE_FORM pins the form of the TD update (0 = writer lists, 1 = per-step sort, 3 = target pipeline, 5 = one-pass form); all must
     reproduce the oracle bit for bit, also when hundreds of agents herd on one row (or all of them on three rows)."""
     monkeypatch.setenv("QE_FORM", form)
     seed = 9
@@ -166,7 +166,7 @@ def test_all_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form,
     try:
         r.steps(steps // 2)
         r.steps(steps - steps // 2)
-        assert capi.lib().qe_fused_form(r.h) == (4 if (form == "3" and N <= 256) else int(form))  # batches of <= 256 agents: the one-CTA loop
+        assert capi.lib().qe_fused_form(r.h) == (4 if (form in ("3", "5") and N <= 256) else int(form))  # batches of <= 256 agents: the one-CTA loop
         assert np.array_equal(r.states.cpu().numpy(), st_o)
         assert np.array_equal(r.ep.cpu().numpy(), rew_o)
         assert np.array_equal(r.table(), q_o)
@@ -199,7 +199,7 @@ def test_automatic_form_selection_switches_forms_and_stays_exact(capi, monkeypat
     monkeypatch.delenv("QE_SORTED", raising=False)
     monkeypatch.setenv("QE_FORM", "2")
     S, A, N, launches, k, seed = 4000, 16, 60_000, 32, 1, 4
-    q_o, st_o, rew_o, _ = _oracle(S, A, N, launches * k + 6, seed, 1)
+    q_o, st_o, rew_o, _ = _oracle(S, A, N, launches * k + 12, seed, 1)
     r = Run(capi, S, A, N, seed, 1)
     try:
         forms = []
@@ -220,6 +220,13 @@ def test_automatic_form_selection_switches_forms_and_stays_exact(capi, monkeypat
         capi.check(capi.lib().qe_set_fused_form(r.h, 3))
         r.steps(2)
         assert capi.lib().qe_fused_form(r.h) == 3
+        capi.check(capi.lib().qe_set_fused_form(r.h, 5))
+        r.steps(1)
+        r.steps(3)
+        assert capi.lib().qe_fused_form(r.h) == 5
+        capi.check(capi.lib().qe_set_fused_form(r.h, 3))
+        r.steps(2)
+        assert capi.lib().qe_fused_form(r.h) == 3
         with pytest.raises(ValueError):
             capi.check(capi.lib().qe_set_fused_form(r.h, 4))
         assert np.array_equal(r.states.cpu().numpy(), st_o)
@@ -229,7 +236,7 @@ def test_automatic_form_selection_switches_forms_and_stays_exact(capi, monkeypat
         r.close()
 
 
-@pytest.mark.parametrize("form", ["3", "1", "0"])
+@pytest.mark.parametrize("form", ["5", "3", "1", "0"])
 def test_config3_long_run_every_form_vs_oracle(capi, monkeypatch, form):
     """2^20 agents x 72 vector steps (the bench window and beyond; the agents herd: rows with dozens of writers),
     every form of the exact update pinned, bit-exact against the C oracle."""
