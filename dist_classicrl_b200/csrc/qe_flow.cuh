@@ -247,13 +247,102 @@ __device__ __forceinline__ void flow_local_pass(int (*whist)[kRadix], int* s_wsu
     __syncthreads();
 }
 
-// ---- the buckets of this block: sort by the low bits, then positions, segment bounds and fresh writer records
+// ---- one warp, one bucket: stable counting pass over [lo, hi) of src -> dst with the warp's own counters (no block
+// barrier).  The LAST pass also writes position and fresh writer record of every element, and -- when it is the only
+// pass, so that a digit IS a state of the bucket -- the segment bounds straight from the digit counts.
+__device__ __forceinline__ void flow_warp_pass(int* cnt, const int2* src, int2* dst, int lo, int hi, int shift, int bits, bool last,
+                                               bool bounds, int32_t key_hi, const FlowScratch& X) {
+    const int lane = threadIdx.x & 31;
+    const int nd = 1 << bits;
+    const uint32_t dm = (uint32_t)nd - 1u;
+    for (int d = lane; d < nd; d += 32) cnt[d] = 0;
+    __syncwarp();
+    for (int base = lo; base < hi; base += 256) {  // eight loads in flight per lane
+        int32_t kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kk[u] = base + 32 * u + lane < hi ? __ldcg(&src[base + 32 * u + lane].x) : 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + 32 * u + lane < hi) atomicAdd(&cnt[((uint32_t)kk[u] >> shift) & dm], 1);
+    }
+    __syncwarp();
+    int run = lo;
+    for (int j = 0; j < nd; j += 32) {  // exclusive scan in digit order, digit j + lane
+        const int d = j + lane;
+        const int v = d < nd ? cnt[d] : 0;
+        const int incl = warp_incl_scan(v);
+        const int first = run + incl - v;
+        if (d < nd) cnt[d] = first;
+        if (bounds && v > 0) X.seg[key_hi | d] = make_uint2((uint32_t)first, (uint32_t)(first + v));
+        run += __shfl_sync(kFull, incl, 31);
+    }
+    __syncwarp();
+    for (int base = lo; base < hi; base += 256) {
+        int2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] = base + 32 * u + lane < hi ? __ldcg(src + base + 32 * u + lane) : make_int2(0, 0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (base + 32 * u >= hi) break;  // (uniform)
+            const bool act = base + 32 * u + lane < hi;
+            const uint32_t d = ((uint32_t)e[u].x >> shift) & dm;
+            const uint32_t peers = digit_peers(d, act);
+            if (act) {
+                const int q = cnt[d] + __popc(peers & ((1u << lane) - 1u));
+                dst[q] = e[u];
+                if (last) { X.pos[e[u].y] = q; X.rec[q] = (uint64_t)(uint32_t)e[u].y; }
+            }
+            __syncwarp();
+            if (act && lane == (__ffs(peers) - 1)) cnt[d] += __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+}
+
+// ---- the buckets of this block: sort by the low bits, then positions, segment bounds and fresh writer records.  A
+// bucket of ordinary size belongs to ONE warp (all buckets of the grid are in flight at once, no block barriers);
+// the few that herding makes large are done afterwards by the whole block.
+constexpr int kWarpBucketMax = 6144;
 template <int WARPS>
 __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], const int* s_base, int* s_wsum, const FlowScratch& X) {
     const int L = X.local_passes;
-    for (int d = blockIdx.x; d < kRadix; d += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x, nb = gridDim.x;
+    bool big = false;
+    for (int j = warp; j * nb + b < kRadix; j += WARPS) {
+        const int d = j * nb + b;
         const int lo = s_base[d], hi = s_base[d + 1];
-        if (hi <= lo) continue;  // (uniform)
+        if (hi <= lo) continue;
+        if (hi - lo > kWarpBucketMax) { big = true; continue; }
+        int src = L & 1;
+        for (int ps = 0; ps < L; ++ps) {
+            const int shift = ps * kRadixBits;
+            flow_warp_pass(whist[warp], X.kv[src], X.kv[src ^ 1], lo, hi, shift, min(kRadixBits, X.msd_shift - shift), ps == L - 1, L == 1,
+                           (int32_t)((uint32_t)d << X.msd_shift), X);
+            src ^= 1;
+        }
+        const int2* fin = X.kv[0];
+        if (L == 0) {  // the bucket is one state, already in place
+            if (lane == 0) X.seg[d] = make_uint2((uint32_t)lo, (uint32_t)hi);
+            for (int q = lo + lane; q < hi; q += 32) {
+                const int2 e = __ldcg(fin + q);
+                X.pos[e.y] = q;
+                X.rec[q] = (uint64_t)(uint32_t)e.y;
+            }
+        } else if (L > 1) {  // bounds from the neighbours in the finished order
+            for (int q = lo + lane; q < hi; q += 32) {
+                const int32_t k = __ldcg(&fin[q].x);
+                const int32_t prev = q > lo ? __ldcg(&fin[q - 1].x) : -1, next = q + 1 < hi ? __ldcg(&fin[q + 1].x) : -1;
+                if (prev != k) X.seg[k].x = (uint32_t)q;
+                if (next != k) X.seg[k].y = (uint32_t)(q + 1);
+            }
+        }
+    }
+    if (!__syncthreads_or(big)) return;
+    for (int d = b; d < kRadix; d += nb) {
+        const int lo = s_base[d], hi = s_base[d + 1];
+        if (hi - lo <= kWarpBucketMax) continue;  // (uniform)
         int src = L & 1;
         for (int ps = 0; ps < L; ++ps) {
             const int shift = ps * kRadixBits;
@@ -269,12 +358,13 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], const int* s_
             if (prev != e.x) X.seg[e.x].x = (uint32_t)q;
             if (next != e.x) X.seg[e.x].y = (uint32_t)(q + 1);
         }
+        __syncthreads();
     }
 }
 
 __host__ __device__ constexpr int flow_row_words(int lpr) { return 8 * lpr + 4; }  // one replayed row per thread, 16-byte aligned, conflict-free
 __host__ __device__ constexpr size_t flow_smem_bytes(int lpr) {
-    return sizeof(int) * ((size_t)8 * kRadix + kRadix + 8) + sizeof(float) * (size_t)flow_row_words(lpr) * 256;
+    return sizeof(int) * ((size_t)8 * kRadix + kRadix + 8) + sizeof(uint4) * 8 * 32 + sizeof(float) * (size_t)flow_row_words(lpr) * 256;
 }
 #ifndef QE_FLOW_MIN_BLOCKS
 #define QE_FLOW_MIN_BLOCKS 3
@@ -290,7 +380,8 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
     extern __shared__ __align__(16) unsigned char s_raw[];  // flow_smem_bytes(LPR)
     int (*s_whist)[kRadix] = reinterpret_cast<int (*)[kRadix]>(s_raw);            // [8][kRadix] per-warp digit counters
     int* s_base = reinterpret_cast<int*>(s_raw) + WARPS * kRadix;                 // [kRadix + 1] bucket starts
-    float* s_rows = reinterpret_cast<float*>(s_base + kRadix + 8);                // in-order pass: [256][RS]; commit: [8*LPR][256] + [256]
+    uint4* s_queue = reinterpret_cast<uint4*>(s_base + kRadix + 8);               // [8][32] per-warp queues of stepped agents
+    float* s_rows = reinterpret_cast<float*>(s_queue + WARPS * 32);               // in-order pass: [256][RS]; commit: [8*LPR][256] + [256]
     float* s_row = s_rows;
     uint32_t* s_touch = reinterpret_cast<uint32_t*>(s_rows) + 8 * LPR * 256;
     static_assert((8 * LPR + 1) * 256 <= RS * 256, "the commit's columns fit in the rows region");
@@ -362,153 +453,177 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                 }
                 return m;
             };
+            // Lanes and chunks are decoupled: the warp selects and steps a whole chunk at a time (all 32 lanes, whatever they
+            // hold) and leaves its agents in a 32-entry queue in shared memory; a lane keeps its agent until the target is
+            // published and then takes the next one from the queue, so an agent that waits for a predecessor holds up one
+            // lane, not a chunk.
+            uint4* myq = s_queue + warp * 32;  // {next state, sorted position, reward bits, action | done << 7}
             int cb = claim_chunk();
             int s_nx = 0, pos_nx = 0;
             if (cb + lane < n) { s_nx = cur[cb + lane]; pos_nx = X.pos[cb + lane]; }
-            int cbn = claim_chunk();
+            int cbn = claim_chunk(), cbnn = claim_chunk();  // (two claims ahead: the counter's round trip stays off the critical path)
             const uint64_t t_start = global_ns();
-            bool aborted = false;
-            while (cb < n && !aborted) {
-                const int i = cb + lane;
-                const bool active = i < n;
-                const int s = s_nx, mypos = pos_nx;
-                if (cbn + lane < n) { s_nx = cur[cbn + lane]; pos_nx = X.pos[cbn + lane]; }
-                uint32_t ew = 0u, valid = 0u, bits1 = 0u;
-                bool explore = false;
-                if (active) {
-                    if (ENV != 0) ew = F.envw[i];
-                    valid = F.use_masks ? env_mask<ENV>(s, ew, T.A, F.env_seed) : full;
-                    explore = (uint64_t)U.draw(i, 0) < thresh;
-                    bits1 = U.draw(i, 1);
-                }
-                int32_t s2 = s;
-                float r = 0.0f;
-                bool term = false;
-                int a;
-                {
-                    RowGather<LPR> rows;
-                    rows.issue(T, s, active);
-                    float mx;
-                    uint32_t tie;
-                    rows.row_max_tie(valid, mx, tie);
-                    a = pick_action(T.A, valid, tie, explore, F.empty_all != 0, bits1);
-                }
-                if (active && a < 0) { atomicOr(T.err, kErrEmpty); a = 0; }
-                a = max(a, 0);
-                if (active) {
-                    if (ENV == 0) mdp_step(s2, a, (uint32_t)F.S, T.A, F.env_seed, F.term_thresh, U.draw(i, 2), U.draw(i, 3), r, term);
-                    else if (ENV == 1) {
-                        if (!ttt_step(ew, a, U.draw(i, 2), U.draw(i, 3), U.draw(i, 4), r, term)) atomicOr(T.err, kErrInvalidMove);
-                        s2 = ttt_state(ew & 0x3FFFFu);
-                    } else {
-                        r = (float)a;
-                        ew += 1u;
-                        term = ew >= F.episode_len;
-                        if (term) ew = 0u;
-                        s2 = 0;
+            if (cb >= n && lane == 0) atomicAdd(X.ctr + 1, 1u);  // a warp without work: its "all my chunks are stepped" arrival
+            int q_base = 0, q_next = 0, q_rem = 0;
+            bool busy = false;
+            int i = 0, mypos = 0;
+            float r = 0.0f;
+            uint32_t m2 = 0u, p = 0u, pe = 0u, head = 0u;
+            for (uint32_t spins = 0;; ++spins) {
+                // ---- produce: the queue is empty -> select + environment step of the next chunk
+                if (q_rem == 0 && cb < n) {
+                    const int ia = cb + lane;
+                    const bool active = ia < n;
+                    const int s = s_nx, pos_a = pos_nx;
+                    if (cbn + lane < n) { s_nx = cur[cbn + lane]; pos_nx = X.pos[cbn + lane]; }
+                    uint32_t ew = 0u, valid = 0u, bits1 = 0u;
+                    bool explore = false;
+                    if (active) {
+                        if (ENV != 0) ew = F.envw[ia];
+                        valid = F.use_masks ? env_mask<ENV>(s, ew, T.A, F.env_seed) : full;
+                        explore = (uint64_t)U.draw(ia, 0) < thresh;
+                        bits1 = U.draw(ia, 1);
                     }
-                    nxt[i] = s2;
-                    if (ENV != 0) F.envw[i] = ew;
-                    float acc = F.ep_ret[i] + r;
-                    float fin = __int_as_float(0x7FC00000);
-                    if (term) { fin = acc; loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
-                    F.ep_ret[i] = acc;
-                    const size_t o = (size_t)k * n + i;
-                    if (F.trace_actions) F.trace_actions[o] = a;
-                    if (F.trace_rewards) F.trace_rewards[o] = r;
-                    if (F.trace_term) F.trace_term[o] = term;
-                    if (F.trace_next) F.trace_next[o] = s2;
-                    if (F.trace_epret) F.trace_epret[o] = fin;
+                    int32_t s2 = s;
+                    float ra = 0.0f;
+                    bool term = false;
+                    int a;
+                    {
+                        RowGather<LPR> rows;
+                        rows.issue(T, s, active);
+                        float mx;
+                        uint32_t tie;
+                        rows.row_max_tie(valid, mx, tie);
+                        a = pick_action(T.A, valid, tie, explore, F.empty_all != 0, bits1);
+                    }
+                    if (active && a < 0) { atomicOr(T.err, kErrEmpty); a = 0; }
+                    a = max(a, 0);
+                    if (active) {
+                        if (ENV == 0) mdp_step(s2, a, (uint32_t)F.S, T.A, F.env_seed, F.term_thresh, U.draw(ia, 2), U.draw(ia, 3), ra, term);
+                        else if (ENV == 1) {
+                            if (!ttt_step(ew, a, U.draw(ia, 2), U.draw(ia, 3), U.draw(ia, 4), ra, term)) atomicOr(T.err, kErrInvalidMove);
+                            s2 = ttt_state(ew & 0x3FFFFu);
+                        } else {
+                            ra = (float)a;
+                            ew += 1u;
+                            term = ew >= F.episode_len;
+                            if (term) ew = 0u;
+                            s2 = 0;
+                        }
+                        nxt[ia] = s2;
+                        if (ENV != 0) F.envw[ia] = ew;
+                        float acc = F.ep_ret[ia] + ra;
+                        float fin = __int_as_float(0x7FC00000);
+                        if (term) { fin = acc; loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
+                        F.ep_ret[ia] = acc;
+                        const size_t o = (size_t)k * n + ia;
+                        if (F.trace_actions) F.trace_actions[o] = a;
+                        if (F.trace_rewards) F.trace_rewards[o] = ra;
+                        if (F.trace_term) F.trace_term[o] = term;
+                        if (F.trace_next) F.trace_next[o] = s2;
+                        if (F.trace_epret) F.trace_epret[o] = fin;
+                        // a terminated agent bootstraps from nothing (QLO:760-766): final at once; a self loop says so
+                        const uint32_t ha = (uint32_t)ia | ((uint32_t)a << 24);
+                        if (term) st_relaxed_rec(rec + pos_a, ha | kRecFinal, __float_as_uint(td_target_s(ra, 0.0f, F.gamma)));
+                        else if (s2 == s) st_relaxed_rec(rec + pos_a, ha | kRecSelf, __float_as_uint(ra));
+                    }
+                    myq[lane] = make_uint4((uint32_t)s2, (uint32_t)pos_a, __float_as_uint(ra), (uint32_t)a | ((term || !active) ? 0x80u : 0u));
+                    __syncwarp();
+                    // the warp's last chunk: all its next states are in place (the bucket counts wait for every warp's arrival)
+                    if (cbn >= n && lane == 0) { __threadfence(); atomicAdd(X.ctr + 1, 1u); }
+                    q_base = cb; q_next = 0; q_rem = min(32, n - cb);
+                    cb = cbn;
+                    cbn = cbnn;
+                    cbnn = claim_chunk();
                 }
-                __syncwarp();
-                if (lane == 0) { __threadfence(); atomicAdd(X.ctr + 1, 1u); }  // this chunk's next states are in place (bucket counts wait for all of them)
-
-                // ---- targets.  A terminated agent bootstraps from nothing (QLO:760-766): final at once; a self loop says so
-                const bool need = active && !term;
-                const uint32_t head = (uint32_t)i | ((uint32_t)a << 24);
-                uint32_t m2 = 0u;
+                // ---- consume: the free lanes take the next agents of the queue, in order (in batches: this is divergent
+                // code); their bootstrap row and segment bounds are fetched now and used at the end of this pass
+                const uint32_t freeb = __ballot_sync(kFull, !busy);
+                bool fresh = false;
                 uint2 sg = make_uint2(0u, 0u);
-                if (active && term) st_relaxed_rec(rec + mypos, head | kRecFinal, __float_as_uint(td_target_s(r, 0.0f, F.gamma)));
-                if (need) {
-                    if (s2 == s) st_relaxed_rec(rec + mypos, head | kRecSelf, __float_as_uint(r));
-                    m2 = F.use_masks ? state_mask<ENV>(s2, T.A, F.env_seed, full) : full;
-                    if (m2 == 0u) atomicOr(T.err, kErrEmpty);  // np.max of an empty selection (QLO:764)
-                    sg = __ldcg(X.seg + s2);
-                }
-                {   // bootstrap rows, transposed gather: the LPR lanes of a group deposit one agent's row (illegal cells at -inf) in its owner's slot
-                    RowGather<LPR> rows;
-                    rows.issue(T, s2, need);
-                    constexpr int G = 32 / LPR;
-                    const int l = lane & (LPR - 1), g = lane / LPR;
+                F8 rowv[LPR];
+                if (q_rem > 0 && (__popc(freeb) >= 8 || (freeb != 0u && (spins & 3u) == 0u))) {
+                    const int idx = q_next + __popc(freeb & ((1u << lane) - 1u));
+                    if (!busy && idx < q_next + q_rem) {
+                        const uint4 d = myq[idx];
+                        if (!(d.w & 0x80u)) {
+                            i = q_base + idx; mypos = (int)d.y; r = __uint_as_float(d.z);
+                            head = (uint32_t)i | ((d.w & 31u) << 24);
+                            const int y = (int)d.x;
+                            m2 = F.use_masks ? state_mask<ENV>(y, T.A, F.env_seed, full) : full;
+                            if (m2 == 0u) atomicOr(T.err, kErrEmpty);  // np.max of an empty selection (QLO:764)
+                            sg = __ldcg(X.seg + y);
+                            const float* row = T.q + (size_t)y * T.ld;
 #pragma unroll
-                    for (int q = 0; q < LPR; ++q) {
-                        const int owner = q * G + g;
-                        const uint32_t mo = (__shfl_sync(kFull, m2, owner) >> (8 * l)) & 0xFFu;
+                            for (int c = 0; c < LPR; ++c) rowv[c] = ld_row8(row + 8 * c);
+                            fresh = busy = true;
+                        }
+                    }
+                    const int took = min(__popc(freeb), q_rem);
+                    q_next += took;
+                    q_rem -= took;
+                }
+                // ---- poll: the (up to four) records of the aligned 32-byte group at the cursor, in position (= agent) order
+                if (busy && !fresh) {
+                    const uint32_t pa = p & ~3u;
+                    const U8 e4 = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa));
+                    bool go = true, fin = false;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t ex = e4.w[2 * j], ey = e4.w[2 * j + 1];
+                        if (go && pa + j >= p) {
+                            if (pa + j >= pe || (int)(ex & kRecAgent) >= i) {
+                                fin = true;  // the segment ends here, or the writers from here on come after i
+                                go = false;
+                            } else if (ex & (kRecFinal | kRecSelf)) {
+                                const float tg = (ex & kRecFinal) ? __uint_as_float(ey) : td_target_s(__uint_as_float(ey), row_max(), F.gamma);
+                                const uint32_t a2 = (ex >> 24) & 31u;
+                                if ((m2 >> a2) & 1u) {  // an illegal cell stays at -inf: it cannot be the masked max
+                                    float* cell = myrow + a2;
+                                    *cell = td_from_target_s(*cell, tg, lr);
+                                }
+                                ++p;
+                            } else {
+                                go = false;  // an earlier writer that has not published yet
+                            }
+                        }
+                    }
+                    if (go && p >= pe) fin = true;
+                    if (fin) {
+                        st_relaxed_rec(rec + mypos, head | kRecFinal, __float_as_uint(td_target_s(r, row_max(), F.gamma)));
+                        busy = false;
+                    }
+                }
+                // ---- the lanes that took an agent in this pass: masked row into shared memory, cursor at the segment's start
+                if (fresh) {
+#pragma unroll
+                    for (int c = 0; c < LPR; ++c) {
                         float w8[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) w8[j] = ((mo >> j) & 1u) ? rows.v[q].v[j] : -INFINITY;
-                        float4* dst = reinterpret_cast<float4*>(s_rows + (wbase + owner) * RS + 8 * l);
-                        dst[0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
-                        dst[1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                        for (int j = 0; j < 8; ++j) w8[j] = ((m2 >> (8 * c + j)) & 1u) ? rowv[c].v[j] : -INFINITY;
+                        reinterpret_cast<float4*>(myrow)[2 * c] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+                        reinterpret_cast<float4*>(myrow)[2 * c + 1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                    }
+                    p = sg.x; pe = sg.y;
+                    if (!(p < pe && pe <= (uint32_t)n)) p = pe = 0u;
+                    if (p >= pe) {  // nobody stands on s': the row is as the table has it
+                        st_relaxed_rec(rec + mypos, head | kRecFinal, __float_as_uint(td_target_s(r, row_max(), F.gamma)));
+                        busy = false;
                     }
                 }
-                __syncwarp();
-                uint32_t p = sg.x, pe = sg.y;
-                if (!(p < pe && pe <= (uint32_t)n)) p = pe = 0u;
-                bool busy = need;
-                for (uint32_t spins = 0; __any_sync(kFull, busy); ++spins) {
-                    if (busy) {
-                        bool fin = p >= pe;
-                        if (!fin) {
-                            const uint32_t pa = p & ~3u;
-                            const U8 ea = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa));
-                            U8 eb;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) eb.w[j] = 0xFFFFFFFFu;  // (agent ids beyond every i: the scan stops there)
-                            if (pa + 4 < pe) eb = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa + 4));
-                            bool stop = false;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const uint32_t ex = j < 4 ? ea.w[2 * j] : eb.w[2 * (j - 4)], ey = j < 4 ? ea.w[2 * j + 1] : eb.w[2 * (j - 4) + 1];
-                                if (!stop && !fin && pa + j >= p) {
-                                    if (pa + j >= pe || (int)(ex & kRecAgent) >= i) {
-                                        fin = true;  // the segment ends here, or the writers from here on come after i
-                                    } else if (ex & (kRecFinal | kRecSelf)) {
-                                        const float tg = (ex & kRecFinal) ? __uint_as_float(ey) : td_target_s(__uint_as_float(ey), row_max(), F.gamma);
-                                        const uint32_t a2 = (ex >> 24) & 31u;
-                                        if ((m2 >> a2) & 1u) {  // an illegal cell stays at -inf: it cannot be the masked max
-                                            float* cell = myrow + a2;
-                                            *cell = td_from_target_s(*cell, tg, lr);
-                                        }
-                                        ++p;
-                                    } else {
-                                        stop = true;  // an earlier writer that has not published yet
-                                    }
-                                }
-                            }
-                            if (!stop && p >= pe) fin = true;
-                        }
-                        if (fin) {
-                            st_relaxed_rec(rec + mypos, head | kRecFinal, __float_as_uint(td_target_s(r, row_max(), F.gamma)));
-                            busy = false;
-                        }
-                    }
-                    if ((spins & 255u) == 255u) {  // (all lanes take the same way out)
-                        if (__any_sync(kFull, ld_relaxed_u32(X.ctr + 4) != 0u || global_ns() - t_start > kPipeTimeoutNs)) {
-                            atomicExch(X.ctr + 4, 1u);
-                            atomicOr(T.err, kErrTimeout);
-                            aborted = true;
-                            break;
-                        }
+                if (cb >= n && q_rem == 0 && !__any_sync(kFull, busy)) break;
+                if ((spins & 255u) == 255u) {  // (all lanes take the same way out)
+                    if (__any_sync(kFull, ld_relaxed_u32(X.ctr + 4) != 0u || global_ns() - t_start > kPipeTimeoutNs)) {
+                        atomicExch(X.ctr + 4, 1u);
+                        atomicOr(T.err, kErrTimeout);
+                        break;
                     }
                 }
-                cb = cbn;
-                cbn = claim_chunk();
             }
             // ---- tail: once every chunk has been selected and stepped, the bucket counts of this block's part of the next states
             __syncthreads();
             if (threadIdx.x == 0) {
-                for (uint32_t spins = 0; ld_relaxed_u32(X.ctr + 1) < (unsigned int)ntiles; ++spins) {
+                for (uint32_t spins = 0; ld_relaxed_u32(X.ctr + 1) < (unsigned int)(nthreads >> 5); ++spins) {
                     __nanosleep(64);
                     if ((spins & 255u) == 255u && (ld_relaxed_u32(X.ctr + 4) != 0u || global_ns() - t_start > kPipeTimeoutNs)) {
                         atomicExch(X.ctr + 4, 1u);
