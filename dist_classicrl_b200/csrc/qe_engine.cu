@@ -331,7 +331,7 @@ int qe_set_fused_form(qe_engine_t* e, int32_t form) {
 }
 int qe_debug_counters(qe_engine_t* e, uint64_t* out8_host, int32_t reset) {
     std::lock_guard<std::mutex> lk(e->mu);
-    if (e->current == 3 && e->P.ctr) {  // the pipelined form: ctr[8..15] of the last launch
+    if ((e->current == 3 || e->current == 5) && e->P.ctr) {  // the pipelined forms: ctr[8..15] of the last launch
         unsigned int h[56];
         CK(cudaMemcpy(h, e->P.ctr + 8, sizeof(h), cudaMemcpyDeviceToHost));
         for (int i = 0; i < 8; ++i) out8_host[i] = h[i];
@@ -910,6 +910,7 @@ static int launch_fused(qe_engine* e, FusedArgs& F, cudaStream_t st) {
         }
         X.sorted_valid = (e->pipe_valid && e->pipe_states == F.st_a && e->pipe_n == F.n && !getenv("QE_PIPE_RESORT")) ? 1 : 0;
         X.old_n = e->pipe_sorted_n;
+        X.flags = getenv("QE_FLOW_FLAGS") ? atoi(getenv("QE_FLOW_FLAGS")) : 0;
         CK(cudaMemsetAsync(e->P.ctr, 0, 64 * sizeof(unsigned int), st));
         void* args[] = {&T, &F, &X};
         CK(cudaLaunchCooperativeKernel((void*)fused_flow_kernel<ENV, LPR>, dim3(blocks), dim3(256), args, smem, st));

@@ -48,8 +48,14 @@ struct FlowScratch {
     int local_passes;     // LSD passes (kRadixBits each) over the low msd_shift bits inside a bucket
     int sorted_valid;     // pos / seg / kv[0] / rec describe the states this launch starts from (to be checked)
     int old_n;            // agents of the order kv[0] and seg[] still describe (0: none, seg[] is all-empty)
+    int flags;            // development switches (QE_FLOW_FLAGS): 1 = no shared-memory staging in the bucket sorts
 };
 
+// counter += 1 in shared memory, address space stated (through a pointer the compiler cannot trace to shared memory a plain
+// atomicAdd becomes a generic atomic, which crawls when the 32 lanes hit one address: a herded row in a bucket)
+__device__ __forceinline__ void smem_inc(int* p) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+}
 __device__ __forceinline__ void st_relaxed_rec(uint64_t* p, uint32_t x, uint32_t y) {
     st_relaxed_u64(p, (uint64_t)x | ((uint64_t)y << 32));
 }
@@ -82,7 +88,7 @@ __device__ __forceinline__ void flow_hist(int (*whist)[kRadix], const int32_t* s
         for (int u = 0; u < 8; ++u) kk[u] = base + 32 * u + lane < hi ? __ldcg(states + base + 32 * u + lane) : 0;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (base + 32 * u + lane < hi) atomicAdd(&whist[warp][(uint32_t)kk[u] >> sh], 1);
+            if (base + 32 * u + lane < hi) smem_inc(&whist[warp][(uint32_t)kk[u] >> sh]);
     }
     __syncthreads();
     for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
@@ -193,7 +199,7 @@ __device__ __forceinline__ void flow_local_pass(int (*whist)[kRadix], int* s_wsu
     __syncwarp();
     for (int base = wlo; base < whi; base += 32) {
         const int x = base + lane;
-        if (x < whi) atomicAdd(&whist[warp][((uint32_t)__ldcg(&src[x].x) >> shift) & dm], 1);
+        if (x < whi) smem_inc(&whist[warp][((uint32_t)__ldcg(&src[x].x) >> shift) & dm]);
     }
     __syncthreads();
     {   // digit totals, exclusive scan over the digits (thread t owns `per` consecutive digits), first free position per (digit, warp)
@@ -263,7 +269,7 @@ __device__ __forceinline__ void flow_warp_pass(int* cnt, const int2* src, int2* 
         for (int u = 0; u < 8; ++u) kk[u] = base + 32 * u + lane < hi ? __ldcg(&src[base + 32 * u + lane].x) : 0;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (base + 32 * u + lane < hi) atomicAdd(&cnt[((uint32_t)kk[u] >> shift) & dm], 1);
+            if (base + 32 * u + lane < hi) smem_inc(&cnt[((uint32_t)kk[u] >> shift) & dm]);
     }
     __syncwarp();
     int run = lo;
@@ -300,25 +306,96 @@ __device__ __forceinline__ void flow_warp_pass(int* cnt, const int2* src, int2* 
     __syncwarp();
 }
 
+// ---- one warp, one bucket, one pass (the low bits are one digit): the bucket is staged in shared memory first, so global
+// memory is read once with every load in flight and the counting / ranking loops run out of shared memory.
+__device__ __forceinline__ void flow_warp_staged(int* cnt, int2* stage, const int2* src, int2* dst, int lo, int hi, int bits, int32_t key_hi,
+                                                 const FlowScratch& X) {
+    const int lane = threadIdx.x & 31;
+    const int nd = 1 << bits, m = hi - lo;
+    const uint32_t dm = (uint32_t)nd - 1u;
+    for (int d = lane; d < nd; d += 32) cnt[d] = 0;
+    for (int base = 0; base < m; base += 256) {
+        int2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] = base + 32 * u + lane < m ? __ldcg(src + lo + base + 32 * u + lane) : make_int2(0, 0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + 32 * u + lane < m) stage[base + 32 * u + lane] = e[u];
+    }
+    __syncwarp();
+    for (int x = lane; x < m; x += 32) smem_inc(&cnt[(uint32_t)stage[x].x & dm]);
+    __syncwarp();
+    int run = lo;
+    for (int j = 0; j < nd; j += 32) {  // exclusive scan in digit order (digit j + lane); a digit is a state: its bounds
+        const int d = j + lane;
+        const int v = d < nd ? cnt[d] : 0;
+        const int incl = warp_incl_scan(v);
+        const int first = run + incl - v;
+        if (d < nd) cnt[d] = first;
+        if (v > 0) X.seg[key_hi | d] = make_uint2((uint32_t)first, (uint32_t)(first + v));
+        run += __shfl_sync(kFull, incl, 31);
+    }
+    __syncwarp();
+    for (int base = 0; base < m; base += 32) {
+        const bool act = base + lane < m;
+        int2 e = make_int2(0, 0);
+        if (act) e = stage[base + lane];
+        const uint32_t d = (uint32_t)e.x & dm;
+        const uint32_t peers = digit_peers(d, act);
+        if (act) {
+            const int q = cnt[d] + __popc(peers & ((1u << lane) - 1u));
+            dst[q] = e;
+            X.pos[e.y] = q;
+            X.rec[q] = (uint64_t)(uint32_t)e.y;
+        }
+        __syncwarp();
+        if (act && lane == (__ffs(peers) - 1)) cnt[d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
 // ---- the buckets of this block: sort by the low bits, then positions, segment bounds and fresh writer records.  A
 // bucket of ordinary size belongs to ONE warp (all buckets of the grid are in flight at once, no block barriers);
 // the few that herding makes large are done afterwards by the whole block.
-constexpr int kWarpBucketMax = 6144;
+constexpr int kWarpBucketMax = 3072;
 template <int WARPS>
-__device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], const int* s_base, int* s_wsum, const FlowScratch& X) {
+__device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char* arena, int arena_bytes, const int* s_base, int* s_wsum,
+                                             const FlowScratch& X) {
     const int L = X.local_passes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x, nb = gridDim.x;
+    // at most three buckets per block (the usual grid): warps 0..2 own one each and a third of the arena (counters + staging area)
+    const bool slots = (kRadix - 1) / nb < 3;
+    const int slot_bytes = (arena_bytes / 3) & ~15;
+    const int stage_cap = (slot_bytes - (int)sizeof(int) * kRadix) / (int)sizeof(int2);
+    const int wsh = slots ? ((X.flags & 2) ? 0 : 4) : 0;  // warps 4..6 own the buckets (warp 0 runs several times slower here; QE_FLOW_FLAGS=2: warps 0..2)
+    const int ow = warp - wsh;                                                            // owner index of this warp (0..2 own buckets)
+    int* cnt = slots ? reinterpret_cast<int*>(arena + (size_t)((ow >= 0 && ow < 3) ? ow : 0) * slot_bytes) : whist[warp];
+    int2* stage = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(cnt) + sizeof(int) * kRadix);
     bool big = false;
-    for (int j = warp; j * nb + b < kRadix; j += WARPS) {
+    for (int j = slots ? (ow >= 0 ? ow : WARPS * kRadix) : warp; j * nb + b < kRadix; j += WARPS) {
         const int d = j * nb + b;
         const int lo = s_base[d], hi = s_base[d + 1];
         if (hi <= lo) continue;
         if (hi - lo > kWarpBucketMax) { big = true; continue; }
+        if (L == 1 && slots && hi - lo <= stage_cap && !(X.flags & 1)) {
+            const uint64_t t0 = global_ns();
+            flow_warp_staged(cnt, stage, X.kv[1], X.kv[0], lo, hi, X.msd_shift, (int32_t)((uint32_t)d << X.msd_shift), X);
+            if (lane == 0) {
+                const unsigned int dt = (unsigned int)((global_ns() - t0) >> 6);
+                atomicMax(X.ctr + 8, (dt << 13) | (unsigned int)min(hi - lo, 8191));  // slowest bucket: {ns / 64, size}
+                atomicMax(X.ctr + 11, (dt << 10) | (unsigned int)d);
+                atomicAdd(X.ctr + 16 + min(dt >> 7, 15u), 1u);                      // histogram, 8 us bins
+                if ((dt >> 7) >= 6u) { atomicAdd(X.ctr + 32 + warp, 1u); atomicAdd(X.ctr + 40 + (b * 8) / nb, 1u); atomicAdd(X.ctr + 48 + min((hi - lo) >> 8, 7), 1u); }
+                else atomicAdd(X.ctr + 56 + min((hi - lo) >> 8, 7), 1u);
+            }
+            continue;
+        }
+        const uint64_t t0 = global_ns();
         int src = L & 1;
         for (int ps = 0; ps < L; ++ps) {
             const int shift = ps * kRadixBits;
-            flow_warp_pass(whist[warp], X.kv[src], X.kv[src ^ 1], lo, hi, shift, min(kRadixBits, X.msd_shift - shift), ps == L - 1, L == 1,
+            flow_warp_pass(cnt, X.kv[src], X.kv[src ^ 1], lo, hi, shift, min(kRadixBits, X.msd_shift - shift), ps == L - 1, L == 1,
                            (int32_t)((uint32_t)d << X.msd_shift), X);
             src ^= 1;
         }
@@ -338,8 +415,10 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], const int* s_
                 if (next != k) X.seg[k].y = (uint32_t)(q + 1);
             }
         }
+        if (lane == 0) atomicMax(X.ctr + 9, (unsigned int)(((global_ns() - t0) >> 6) << 13) | (unsigned int)min(hi - lo, 8191));
     }
     if (!__syncthreads_or(big)) return;
+    if (threadIdx.x == 0) atomicAdd(X.ctr + 10, 1u);  // blocks with a large bucket
     for (int d = b; d < kRadix; d += nb) {
         const int lo = s_base[d], hi = s_base[d + 1];
         if (hi - lo <= kWarpBucketMax) continue;  // (uniform)
@@ -378,9 +457,10 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
     __shared__ unsigned int s_cnt[8];
     __shared__ int s_wsum[WARPS];
     extern __shared__ __align__(16) unsigned char s_raw[];  // flow_smem_bytes(LPR)
-    int (*s_whist)[kRadix] = reinterpret_cast<int (*)[kRadix]>(s_raw);            // [8][kRadix] per-warp digit counters
-    int* s_base = reinterpret_cast<int*>(s_raw) + WARPS * kRadix;                 // [kRadix + 1] bucket starts
-    uint4* s_queue = reinterpret_cast<uint4*>(s_base + kRadix + 8);               // [8][32] per-warp queues of stepped agents
+    int* s_base = reinterpret_cast<int*>(s_raw);                                  // [kRadix + 1] bucket starts
+    unsigned char* s_arena = s_raw + sizeof(int) * (kRadix + 8);                  // everything below: carved up anew by the bucket sorts
+    int (*s_whist)[kRadix] = reinterpret_cast<int (*)[kRadix]>(s_arena);          // [8][kRadix] per-warp digit counters
+    uint4* s_queue = reinterpret_cast<uint4*>(s_arena + sizeof(int) * WARPS * kRadix);  // [8][32] per-warp queues of stepped agents
     float* s_rows = reinterpret_cast<float*>(s_queue + WARPS * 32);               // in-order pass: [256][RS]; commit: [8*LPR][256] + [256]
     float* s_row = s_rows;
     uint32_t* s_touch = reinterpret_cast<uint32_t*>(s_rows) + 8 * LPR * 256;
@@ -420,7 +500,7 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
             grid.sync();
             flow_scatter<WARPS>(s_whist, s_base, s_wsum, F.st_a, n, X.kv[X.local_passes & 1], X);
             grid.sync();
-            flow_buckets<WARPS>(s_whist, s_base, s_wsum, X);
+            flow_buckets<WARPS>(s_whist, s_arena, (int)(flow_smem_bytes(LPR) - sizeof(int) * (kRadix + 8)), s_base, s_wsum, X);
             grid.sync();
         }
     }
@@ -458,10 +538,10 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
             // published and then takes the next one from the queue, so an agent that waits for a predecessor holds up one
             // lane, not a chunk.
             uint4* myq = s_queue + warp * 32;  // {next state, sorted position, reward bits, action | done << 7}
-            int cb = claim_chunk();
+            int cb = ((X.flags & 8) && warp == 0) ? n : claim_chunk();  // (development: warp 0 sits the pass out)
             int s_nx = 0, pos_nx = 0;
             if (cb + lane < n) { s_nx = cur[cb + lane]; pos_nx = X.pos[cb + lane]; }
-            int cbn = claim_chunk(), cbnn = claim_chunk();  // (two claims ahead: the counter's round trip stays off the critical path)
+            int cbn = cb >= n ? n : claim_chunk(), cbnn = cb >= n ? n : claim_chunk();  // (two claims ahead: the counter's round trip stays off the critical path)
             const uint64_t t_start = global_ns();
             if (cb >= n && lane == 0) atomicAdd(X.ctr + 1, 1u);  // a warp without work: its "all my chunks are stepped" arrival
             int q_base = 0, q_next = 0, q_rem = 0;
@@ -744,7 +824,7 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
         flow_scatter<WARPS>(s_whist, s_base, s_wsum, nxt, n, X.kv[X.local_passes & 1], X);
         grid.sync();
         if (clk && k < 10) F.phase_ns[32 + k] = global_ns();
-        flow_buckets<WARPS>(s_whist, s_base, s_wsum, X);
+        flow_buckets<WARPS>(s_whist, s_arena, (int)(flow_smem_bytes(LPR) - sizeof(int) * (kRadix + 8)), s_base, s_wsum, X);
         grid.sync();
         if (clk && k < 10) F.phase_ns[3 + 3 * k] = global_ns();
     }
