@@ -226,7 +226,7 @@ def python_port_rate(workload: str, agents: int, steps: int):
 
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 FORM_NAMES = {0: "writer lists", 1: "per-step sort", 3: "target pipeline", 4: "one-CTA loop (small batches)", 5: "one-pass pipeline"}
-FORM_KERNELS = {0: "fused_kernel", 1: "fused_sorted_kernel", 3: "fused_pipe_kernel", 4: "fused_small_kernel"}
+FORM_KERNELS = {0: "fused_kernel", 1: "fused_sorted_kernel", 3: "fused_pipe_kernel", 4: "fused_small_kernel", 5: "fused_flow_kernel"}
 
 
 class TwinEnv:
@@ -684,8 +684,12 @@ def run_ours(args) -> dict | None:
     phases = None
     if m >= 4:
         ks = (m - 1) // 3
-        names = ("select_env_step_us", "target_pipeline_us", "commit_and_sort_us") if form_id == 3 else ("select_step_register_us", "td_first_pass_us", "td_deferred_us")
+        names = {3: ("select_env_step_us", "target_pipeline_us", "commit_and_sort_us"), 5: ("select_step_targets_us", "commit_us", "sort_us")}.get(
+            form_id, ("select_step_register_us", "td_first_pass_us", "td_deferred_us"))
         phases = {name: sum(buf[1 + ph + 3 * j] - buf[ph + 3 * j] for j in range(ks)) / ks / 1e3 for ph, name in enumerate(names)}
+        if form_id == 5:
+            phases["sort_scatter_us"] = sum(buf[32 + j] - buf[2 + 3 * j] for j in range(ks)) / ks / 1e3
+            phases["sort_buckets_us"] = sum(buf[3 + 3 * j] - buf[32 + j] for j in range(ks)) / ks / 1e3
         if form_id == 3:
             phases["commit_us"] = sum(buf[32 + j] - buf[2 + 3 * j] for j in range(ks)) / ks / 1e3
             phases["sort_us"] = sum(buf[3 + 3 * j] - buf[32 + j] for j in range(ks)) / ks / 1e3

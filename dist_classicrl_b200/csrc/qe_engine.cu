@@ -80,7 +80,7 @@ struct qe_engine {
     // The fused loop has two exact forms of the TD update: writer lists (qe_kernels.cuh; best while few agents share
     // a row) and the per-step sort (qe_sorted.cuh; best once agents herd).  Both give identical results, so the engine
     // times its launches and keeps using the faster form, trying the other one every kProbeEvery launches.
-    int strategy = 3;        // 0 = writer lists, 1 = per-step sort, 2 = time both and keep the faster, 3 (default) = target pipeline (QE_FORM / QE_SORTED env)
+    int strategy = 5;        // 0 = writer lists, 1 = per-step sort, 2 = time both and keep the faster, 3 = target pipeline, 5 (default) = one-pass pipeline (QE_FORM / QE_SORTED env)
     int current = 0, since_probe = 0, timed_kind = -1, auto_launches = 0, auto_form = 0;  // state of pick_form (strategy 2)
     double timed_work = 0.0, rate[2] = {0.0, 0.0};  // agent-steps per millisecond of the last timed launch of each form
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -286,8 +286,8 @@ static int create_impl(qe_engine* e, int64_t num_states, int32_t num_actions, fl
         while (bits < 31 && (1ll << bits) < e->S) ++bits;
         e->X.passes = (bits + kRadixBits - 1) / kRadixBits;
     }
-    e->strategy = getenv("QE_FORM") ? atoi(getenv("QE_FORM")) : (getenv("QE_SORTED") ? atoi(getenv("QE_SORTED")) : 3);
-    if (e->strategy < 0 || e->strategy == 4 || e->strategy > 5) e->strategy = 3;
+    e->strategy = getenv("QE_FORM") ? atoi(getenv("QE_FORM")) : (getenv("QE_SORTED") ? atoi(getenv("QE_SORTED")) : 5);
+    if (e->strategy < 0 || e->strategy == 4 || e->strategy > 5) e->strategy = 5;
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     e->T.spill_slots = 1024;

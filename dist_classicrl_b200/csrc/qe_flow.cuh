@@ -524,12 +524,17 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                 if (lane == 0) c = (int)atomicAdd(claim, 1u);
                 return __shfl_sync(kFull, c, 0) * 32;
             };
+            uint32_t m2 = 0u;  // legal actions of the row this lane is replaying (illegal cells never reach the max)
             auto row_max = [&]() {
                 float m = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 2 * LPR; ++c) {
                     const float4 v = reinterpret_cast<const float4*>(myrow)[c];
-                    m = fmaxf(fmaxf(fmaxf(fmaxf(m, v.x), v.y), v.z), v.w);
+                    const uint32_t mm = m2 >> (4 * c);
+                    m = fmaxf(m, (mm & 1u) ? v.x : -INFINITY);
+                    m = fmaxf(m, (mm & 2u) ? v.y : -INFINITY);
+                    m = fmaxf(m, (mm & 4u) ? v.z : -INFINITY);
+                    m = fmaxf(m, (mm & 8u) ? v.w : -INFINITY);
                 }
                 return m;
             };
@@ -546,12 +551,21 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
             if (cb >= n && lane == 0) atomicAdd(X.ctr + 1, 1u);  // a warp without work: its "all my chunks are stepped" arrival
             int q_base = 0, q_next = 0, q_rem = 0;
             bool busy = false;
+#ifdef QE_FLOW_STATS  // development: lane-passes by what the lane did (ctr[24..29], launch totals)
+            uint32_t st_pass = 0, st_busy = 0, st_prog = 0, st_block = 0, st_fresh = 0, st_prod = 0;
+#define FLOW_STAT(x) x
+#else
+#define FLOW_STAT(x)
+#endif
             int i = 0, mypos = 0;
             float r = 0.0f;
-            uint32_t m2 = 0u, p = 0u, pe = 0u, head = 0u;
+            uint32_t p = 0u, pe = 0u, head = 0u;
+            bool fresh = false;  // took its agent in the previous pass: the bootstrap row is on its way into shared memory
             for (uint32_t spins = 0;; ++spins) {
                 // ---- produce: the queue is empty -> select + environment step of the next chunk
+                FLOW_STAT(++st_pass; st_busy += busy ? 1u : 0u;)
                 if (q_rem == 0 && cb < n) {
+                    FLOW_STAT(++st_prod;)
                     const int ia = cb + lane;
                     const bool active = ia < n;
                     const int s = s_nx, pos_a = pos_nx;
@@ -616,13 +630,12 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                     cbn = cbnn;
                     cbnn = claim_chunk();
                 }
-                // ---- consume: the free lanes take the next agents of the queue, in order (in batches: this is divergent
-                // code); their bootstrap row and segment bounds are fetched now and used at the end of this pass
+                // ---- consume: the free lanes take the next agents of the queue, in order.  The bootstrap row travels to the
+                // lane's shared-memory slot asynchronously (cp.async, no registers) and the segment bounds are not looked at
+                // before the next pass: nobody waits for this gather.
                 const uint32_t freeb = __ballot_sync(kFull, !busy);
-                bool fresh = false;
-                uint2 sg = make_uint2(0u, 0u);
-                F8 rowv[LPR];
-                if (q_rem > 0 && (__popc(freeb) >= 8 || (freeb != 0u && (spins & 3u) == 0u))) {
+                bool took_now = false;
+                if (q_rem > 0 && freeb != 0u) {
                     const int idx = q_next + __popc(freeb & ((1u << lane) - 1u));
                     if (!busy && idx < q_next + q_rem) {
                         const uint4 d = myq[idx];
@@ -632,22 +645,34 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                             const int y = (int)d.x;
                             m2 = F.use_masks ? state_mask<ENV>(y, T.A, F.env_seed, full) : full;
                             if (m2 == 0u) atomicOr(T.err, kErrEmpty);  // np.max of an empty selection (QLO:764)
-                            sg = __ldcg(X.seg + y);
+                            const uint2 sg = __ldcg(X.seg + y);
+                            p = sg.x; pe = sg.y;
                             const float* row = T.q + (size_t)y * T.ld;
 #pragma unroll
-                            for (int c = 0; c < LPR; ++c) rowv[c] = ld_row8(row + 8 * c);
-                            fresh = busy = true;
+                            for (int c = 0; c < 2 * LPR; ++c) cp_async16(myrow + 4 * c, row + 4 * c);
+                            fresh = busy = took_now = true;
                         }
                     }
                     const int took = min(__popc(freeb), q_rem);
                     q_next += took;
                     q_rem -= took;
                 }
-                // ---- poll: the (up to four) records of the aligned 32-byte group at the cursor, in position (= agent) order
-                if (busy && !fresh) {
-                    const uint32_t pa = p & ~3u;
-                    const U8 e4 = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa));
+                if (busy && !took_now) {
+                    // ---- poll: the (up to four) records of the aligned 32-byte group at the cursor, in position (= agent) order
                     bool go = true, fin = false;
+                    if (fresh) {
+                        cp_async_wait_all();
+                        fresh = false;
+                        FLOW_STAT(++st_fresh;)
+                        if (!(p < pe && pe <= (uint32_t)n)) p = pe = 0u;
+                        if (p >= pe) { fin = true; go = false; }  // nobody stands on s': the row is as the table has it
+                    }
+                    const uint32_t pa = p & ~3u;
+                    FLOW_STAT(const uint32_t p0 = p;)
+                    U8 e4;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) e4.w[j] = 0u;
+                    if (go) e4 = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa));
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t ex = e4.w[2 * j], ey = e4.w[2 * j + 1];
@@ -658,10 +683,8 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                             } else if (ex & (kRecFinal | kRecSelf)) {
                                 const float tg = (ex & kRecFinal) ? __uint_as_float(ey) : td_target_s(__uint_as_float(ey), row_max(), F.gamma);
                                 const uint32_t a2 = (ex >> 24) & 31u;
-                                if ((m2 >> a2) & 1u) {  // an illegal cell stays at -inf: it cannot be the masked max
-                                    float* cell = myrow + a2;
-                                    *cell = td_from_target_s(*cell, tg, lr);
-                                }
+                                float* cell = myrow + a2;
+                                *cell = td_from_target_s(*cell, tg, lr);
                                 ++p;
                             } else {
                                 go = false;  // an earlier writer that has not published yet
@@ -669,24 +692,8 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                         }
                     }
                     if (go && p >= pe) fin = true;
+                    FLOW_STAT(st_prog += (fin || p != p0) ? 1u : 0u; st_block += (!fin && p == p0) ? 1u : 0u;)
                     if (fin) {
-                        st_relaxed_rec(rec + mypos, head | kRecFinal, __float_as_uint(td_target_s(r, row_max(), F.gamma)));
-                        busy = false;
-                    }
-                }
-                // ---- the lanes that took an agent in this pass: masked row into shared memory, cursor at the segment's start
-                if (fresh) {
-#pragma unroll
-                    for (int c = 0; c < LPR; ++c) {
-                        float w8[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) w8[j] = ((m2 >> (8 * c + j)) & 1u) ? rowv[c].v[j] : -INFINITY;
-                        reinterpret_cast<float4*>(myrow)[2 * c] = make_float4(w8[0], w8[1], w8[2], w8[3]);
-                        reinterpret_cast<float4*>(myrow)[2 * c + 1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
-                    }
-                    p = sg.x; pe = sg.y;
-                    if (!(p < pe && pe <= (uint32_t)n)) p = pe = 0u;
-                    if (p >= pe) {  // nobody stands on s': the row is as the table has it
                         st_relaxed_rec(rec + mypos, head | kRecFinal, __float_as_uint(td_target_s(r, row_max(), F.gamma)));
                         busy = false;
                     }
@@ -700,6 +707,16 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                     }
                 }
             }
+#ifdef QE_FLOW_STATS
+            {
+                const uint32_t a0 = __reduce_add_sync(kFull, st_busy), a1 = __reduce_add_sync(kFull, st_prog), a2 = __reduce_add_sync(kFull, st_block),
+                               a3 = __reduce_add_sync(kFull, st_fresh);
+                if (lane == 0) {
+                    atomicAdd(X.ctr + 24, st_pass); atomicAdd(X.ctr + 25, a0 >> 5); atomicAdd(X.ctr + 26, a1 >> 5); atomicAdd(X.ctr + 27, a2 >> 5);
+                    atomicAdd(X.ctr + 28, a3 >> 5); atomicAdd(X.ctr + 29, st_prod);
+                }
+            }
+#endif
             // ---- tail: once every chunk has been selected and stepped, the bucket counts of this block's part of the next states
             __syncthreads();
             if (threadIdx.x == 0) {

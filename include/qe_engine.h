@@ -231,12 +231,12 @@ uint32_t qe_stream_u32(uint32_t seed, uint32_t t, uint32_t i, uint32_t k);
 int64_t qe_kernel_launches(qe_engine_t* e);     /* kernels launched by this handle so far */
 int32_t qe_fused_grid_blocks(qe_engine_t* e);   /* grid of the last fused launch */
 /* form of the TD update the last fused launch used: 0 = writer lists, 1 = per-step sort, 3 = target pipeline, 4 = one-CTA
- * loop for batches of at most 256 agents (csrc/qe_small.cuh; picked automatically under form 3).  All exact. */
+ * loop for batches of at most 256 agents (csrc/qe_small.cuh; picked automatically under forms 3 and 5), 5 = one-pass
+ * pipeline (csrc/qe_flow.cuh).  All exact. */
 int32_t qe_fused_form(qe_engine_t* e);
 /* Which exact form of the TD update the fused loop uses: 0 = writer lists, 1 = per-step sort, 2 = keep timing those two
- * and use the faster one, 3 = target pipeline (csrc/qe_pipe.cuh; default; QE_FORM in the environment sets the initial
- * value).  All forms give identical results.  The replicated multi-GPU mode pins form 1 on every rank: merged replicas learn G times as fast, agents herd
- * sooner, and ranks that probe at different moments would wait for each other at the all-reduce. */
+ * and use the faster one, 3 = target pipeline (csrc/qe_pipe.cuh), 5 = one-pass pipeline (csrc/qe_flow.cuh; default;
+ * QE_FORM in the environment sets the initial value).  All forms give identical results. */
 int qe_set_fused_form(qe_engine_t* e, int32_t form);
 /* phase clock of the last fused launch (synchronous): out_host[0] = %globaltimer (ns) at kernel start, then for each
  * of the first 10 vector steps the time after phase A (select + env step + writer registration), after phase B1 (TD

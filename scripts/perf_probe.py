@@ -74,6 +74,7 @@ if lib.qe_fused_form(h) == 5 and lib.qe_debug_counters(h, cnt, 0) == 0:
     print('slowest staged bucket: %.1f us, %d keys | slowest unstaged bucket: %.1f us, %d keys | block-path blocks (launch total) %d' % ((cnt[0] >> 13) * 64 / 1e3, cnt[0] & 8191, (cnt[1] >> 13) * 64 / 1e3, cnt[1] & 8191, cnt[2]))
     lib.qe_debug_counters(h, cnt, 2)
     print('slowest bucket id', cnt[3] & 1023, 'duration histogram (8 us bins, launch total):', [cnt[8 + j] for j in range(16)])
+    print('in-order pass (launch totals, warp-passes; lane counts / 32): passes %d busy %d progress %d blocked %d fresh %d produce %d' % tuple(cnt[16 + j] for j in range(6)))
     print('slow by warp', [cnt[24 + j] for j in range(8)], 'by block eighth', [cnt[32 + j] for j in range(8)], 'slow by size/256', [cnt[40 + j] for j in range(8)], 'fast by size/256', [cnt[48 + j] for j in range(8)])
 if lib.qe_fused_form(h) == 3:
     if lib.qe_debug_counters(h, cnt, 2) == 0 and cnt[0]:

@@ -65,7 +65,7 @@ def test_our_arm_prints_the_full_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1 and cb["sample"]
     assert d["atomics_mode"]["value"] > d["value"]  # dropping the ordering guarantee is never slower
-    assert d["config"]["td_update_form"] == "target pipeline" and r["kernel"].startswith("fused_pipe_kernel")
+    assert d["config"]["td_update_form"] == "one-pass pipeline" and r["kernel"].startswith("fused_flow_kernel")
     assert d["config"]["warmup_requested"] == 3 and d["config"]["warmup_used"] == d["warmup"]
     vl = d["value_long"]
     assert 0 < vl["value"] and vl["vector_steps"].startswith("8..") and len(vl["ms_per_step_by_32_step_window"]) >= 15
