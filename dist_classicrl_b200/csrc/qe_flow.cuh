@@ -308,8 +308,8 @@ __device__ __forceinline__ void flow_warp_pass(int* cnt, const int2* src, int2* 
 
 // ---- one warp, one bucket, one pass (the low bits are one digit): the bucket is staged in shared memory first, so global
 // memory is read once with every load in flight and the counting / ranking loops run out of shared memory.
-__device__ __forceinline__ void flow_warp_staged(int* cnt, int2* stage, const int2* src, int2* dst, int lo, int hi, int bits, int32_t key_hi,
-                                                 const FlowScratch& X) {
+__device__ __forceinline__ void flow_warp_staged(int* cnt, int2* stage, uint16_t* order, const int2* src, int2* dst, int lo, int hi, int bits,
+                                                 int32_t key_hi, const FlowScratch& X) {
     const int lane = threadIdx.x & 31;
     const int nd = 1 << bits, m = hi - lo;
     const uint32_t dm = (uint32_t)nd - 1u;
@@ -325,32 +325,34 @@ __device__ __forceinline__ void flow_warp_staged(int* cnt, int2* stage, const in
     __syncwarp();
     for (int x = lane; x < m; x += 32) smem_inc(&cnt[(uint32_t)stage[x].x & dm]);
     __syncwarp();
-    int run = lo;
+    int run = 0;
     for (int j = 0; j < nd; j += 32) {  // exclusive scan in digit order (digit j + lane); a digit is a state: its bounds
         const int d = j + lane;
         const int v = d < nd ? cnt[d] : 0;
         const int incl = warp_incl_scan(v);
         const int first = run + incl - v;
         if (d < nd) cnt[d] = first;
-        if (v > 0) X.seg[key_hi | d] = make_uint2((uint32_t)first, (uint32_t)(first + v));
+        if (v > 0) X.seg[key_hi | d] = make_uint2((uint32_t)(lo + first), (uint32_t)(lo + first + v));
         run += __shfl_sync(kFull, incl, 31);
     }
     __syncwarp();
+    // ranks in shared memory (order[rank] = where the element sits in the staging area) ...
     for (int base = 0; base < m; base += 32) {
         const bool act = base + lane < m;
-        int2 e = make_int2(0, 0);
-        if (act) e = stage[base + lane];
-        const uint32_t d = (uint32_t)e.x & dm;
+        const uint32_t d = act ? ((uint32_t)stage[base + lane].x & dm) : 0u;
         const uint32_t peers = digit_peers(d, act);
-        if (act) {
-            const int q = cnt[d] + __popc(peers & ((1u << lane) - 1u));
-            dst[q] = e;
-            X.pos[e.y] = q;
-            X.rec[q] = (uint64_t)(uint32_t)e.y;
-        }
+        if (act) order[cnt[d] + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)(base + lane);
         __syncwarp();
         if (act && lane == (__ffs(peers) - 1)) cnt[d] += __popc(peers);
         __syncwarp();
+    }
+    // ... so that the finished order and the fresh writer records leave as whole lines; only agent -> position is scattered
+    for (int x = lane; x < m; x += 32) {
+        const int2 e = stage[order[x]];
+        const int q = lo + x;
+        dst[q] = e;
+        X.rec[q] = (uint64_t)(uint32_t)e.y;
+        X.pos[e.y] = q;
     }
 }
 
@@ -367,11 +369,12 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
     // at most three buckets per block (the usual grid): warps 0..2 own one each and a third of the arena (counters + staging area)
     const bool slots = (kRadix - 1) / nb < 3;
     const int slot_bytes = (arena_bytes / 3) & ~15;
-    const int stage_cap = (slot_bytes - (int)sizeof(int) * kRadix) / (int)sizeof(int2);
+    const int stage_cap = min(((slot_bytes - (int)sizeof(int) * kRadix) / (int)(sizeof(int2) + sizeof(uint16_t))) & ~7, 65535);
     const int wsh = slots ? ((X.flags & 2) ? 0 : 4) : 0;  // warps 4..6 own the buckets (warp 0 runs several times slower here; QE_FLOW_FLAGS=2: warps 0..2)
     const int ow = warp - wsh;                                                            // owner index of this warp (0..2 own buckets)
     int* cnt = slots ? reinterpret_cast<int*>(arena + (size_t)((ow >= 0 && ow < 3) ? ow : 0) * slot_bytes) : whist[warp];
     int2* stage = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(cnt) + sizeof(int) * kRadix);
+    uint16_t* order = reinterpret_cast<uint16_t*>(stage + stage_cap);
     bool big = false;
     for (int j = slots ? (ow >= 0 ? ow : WARPS * kRadix) : warp; j * nb + b < kRadix; j += WARPS) {
         const int d = j * nb + b;
@@ -380,7 +383,7 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
         if (hi - lo > kWarpBucketMax) { big = true; continue; }
         if (L == 1 && slots && hi - lo <= stage_cap && !(X.flags & 1)) {
             const uint64_t t0 = global_ns();
-            flow_warp_staged(cnt, stage, X.kv[1], X.kv[0], lo, hi, X.msd_shift, (int32_t)((uint32_t)d << X.msd_shift), X);
+            flow_warp_staged(cnt, stage, order, X.kv[1], X.kv[0], lo, hi, X.msd_shift, (int32_t)((uint32_t)d << X.msd_shift), X);
             if (lane == 0) {
                 const unsigned int dt = (unsigned int)((global_ns() - t0) >> 6);
                 atomicMax(X.ctr + 8, (dt << 13) | (unsigned int)min(hi - lo, 8191));  // slowest bucket: {ns / 64, size}
@@ -443,7 +446,7 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
 
 __host__ __device__ constexpr int flow_row_words(int lpr) { return 8 * lpr + 4; }  // one replayed row per thread, 16-byte aligned, conflict-free
 __host__ __device__ constexpr size_t flow_smem_bytes(int lpr) {
-    return sizeof(int) * ((size_t)8 * kRadix + kRadix + 8) + sizeof(uint4) * 8 * 32 + sizeof(float) * (size_t)flow_row_words(lpr) * 256;
+    return sizeof(int) * ((size_t)8 * kRadix + kRadix + 8) + (sizeof(uint4) + sizeof(uint2)) * 8 * 32 + sizeof(float) * (size_t)flow_row_words(lpr) * 256;
 }
 #ifndef QE_FLOW_MIN_BLOCKS
 #define QE_FLOW_MIN_BLOCKS 3
@@ -461,7 +464,8 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
     unsigned char* s_arena = s_raw + sizeof(int) * (kRadix + 8);                  // everything below: carved up anew by the bucket sorts
     int (*s_whist)[kRadix] = reinterpret_cast<int (*)[kRadix]>(s_arena);          // [8][kRadix] per-warp digit counters
     uint4* s_queue = reinterpret_cast<uint4*>(s_arena + sizeof(int) * WARPS * kRadix);  // [8][32] per-warp queues of stepped agents
-    float* s_rows = reinterpret_cast<float*>(s_queue + WARPS * 32);               // in-order pass: [256][RS]; commit: [8*LPR][256] + [256]
+    uint2* s_qseg = reinterpret_cast<uint2*>(s_queue + WARPS * 32);               // [8][32] segment bounds of the queued agents' next states
+    float* s_rows = reinterpret_cast<float*>(s_qseg + WARPS * 32);                // in-order pass: [256][RS]; commit: [8*LPR][256] + [256]
     float* s_row = s_rows;
     uint32_t* s_touch = reinterpret_cast<uint32_t*>(s_rows) + 8 * LPR * 256;
     static_assert((8 * LPR + 1) * 256 <= RS * 256, "the commit's columns fit in the rows region");
@@ -519,11 +523,13 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
         {
             unsigned int* claim = X.ctr;
             float* myrow = s_rows + threadIdx.x * RS;
-            auto claim_chunk = [&]() {
+            auto claim_raw = [&]() {  // lane 0's answer; nobody waits for it before claim_get
                 int c = 0;
                 if (lane == 0) c = (int)atomicAdd(claim, 1u);
-                return __shfl_sync(kFull, c, 0) * 32;
+                return c;
             };
+            auto claim_get = [&](int c) { return __shfl_sync(kFull, c, 0) * 32; };
+            auto claim_chunk = [&]() { return claim_get(claim_raw()); };
             uint32_t m2 = 0u;  // legal actions of the row this lane is replaying (illegal cells never reach the max)
             auto row_max = [&]() {
                 float m = -INFINITY;
@@ -543,10 +549,13 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
             // published and then takes the next one from the queue, so an agent that waits for a predecessor holds up one
             // lane, not a chunk.
             uint4* myq = s_queue + warp * 32;  // {next state, sorted position, reward bits, action | done << 7}
+            uint2* myqs = s_qseg + warp * 32;  // {start, end} of the segment of the next state
             int cb = ((X.flags & 8) && warp == 0) ? n : claim_chunk();  // (development: warp 0 sits the pass out)
             int s_nx = 0, pos_nx = 0;
-            if (cb + lane < n) { s_nx = cur[cb + lane]; pos_nx = X.pos[cb + lane]; }
-            int cbn = cb >= n ? n : claim_chunk(), cbnn = cb >= n ? n : claim_chunk();  // (two claims ahead: the counter's round trip stays off the critical path)
+            float ep_nx = 0.0f;
+            if (cb + lane < n) { s_nx = cur[cb + lane]; pos_nx = X.pos[cb + lane]; ep_nx = F.ep_ret[cb + lane]; }
+            int cbn = cb >= n ? n : claim_chunk();
+            int cbnn_raw = cb >= n ? (n >> 5) + 1 : claim_raw();  // (two claims ahead, the second one still in flight: the counter's round trip stays off the critical path)
             const uint64_t t_start = global_ns();
             if (cb >= n && lane == 0) atomicAdd(X.ctr + 1, 1u);  // a warp without work: its "all my chunks are stepped" arrival
             int q_base = 0, q_next = 0, q_rem = 0;
@@ -569,7 +578,8 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                     const int ia = cb + lane;
                     const bool active = ia < n;
                     const int s = s_nx, pos_a = pos_nx;
-                    if (cbn + lane < n) { s_nx = cur[cbn + lane]; pos_nx = X.pos[cbn + lane]; }
+                    const float ep_a = ep_nx;
+                    if (cbn + lane < n) { s_nx = cur[cbn + lane]; pos_nx = X.pos[cbn + lane]; ep_nx = F.ep_ret[cbn + lane]; }
                     uint32_t ew = 0u, valid = 0u, bits1 = 0u;
                     bool explore = false;
                     if (active) {
@@ -581,6 +591,7 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                     int32_t s2 = s;
                     float ra = 0.0f;
                     bool term = false;
+                    uint2 sg2 = make_uint2(0u, 0u);
                     int a;
                     {
                         RowGather<LPR> rows;
@@ -605,8 +616,9 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                             s2 = 0;
                         }
                         nxt[ia] = s2;
+                        if (!term) sg2 = __ldcg(X.seg + s2);  // the writers of the row this agent bootstraps from (in flight until the queue entry is written)
                         if (ENV != 0) F.envw[ia] = ew;
-                        float acc = F.ep_ret[ia] + ra;
+                        float acc = ep_a + ra;
                         float fin = __int_as_float(0x7FC00000);
                         if (term) { fin = acc; loc_sum += (double)acc; ++loc_cnt; acc = 0.0f; }
                         F.ep_ret[ia] = acc;
@@ -622,57 +634,56 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                         else if (s2 == s) st_relaxed_rec(rec + pos_a, ha | kRecSelf, __float_as_uint(ra));
                     }
                     myq[lane] = make_uint4((uint32_t)s2, (uint32_t)pos_a, __float_as_uint(ra), (uint32_t)a | ((term || !active) ? 0x80u : 0u));
+                    if (!(sg2.x < sg2.y && sg2.y <= (uint32_t)n)) sg2 = make_uint2(0u, 0u);
+                    myqs[lane] = sg2;
                     __syncwarp();
                     // the warp's last chunk: all its next states are in place (the bucket counts wait for every warp's arrival)
                     if (cbn >= n && lane == 0) { __threadfence(); atomicAdd(X.ctr + 1, 1u); }
                     q_base = cb; q_next = 0; q_rem = min(32, n - cb);
                     cb = cbn;
-                    cbn = cbnn;
-                    cbnn = claim_chunk();
+                    cbn = claim_get(cbnn_raw);
+                    cbnn_raw = claim_raw();
                 }
                 // ---- consume: the free lanes take the next agents of the queue, in order.  The bootstrap row travels to the
-                // lane's shared-memory slot asynchronously (cp.async, no registers) and the segment bounds are not looked at
-                // before the next pass: nobody waits for this gather.
+                // lane's shared-memory slot asynchronously (cp.async, no registers) beside the first poll of the writer records
+                // (the segment bounds came with the queue entry): an agent without unfinished predecessors is done in this pass.
                 const uint32_t freeb = __ballot_sync(kFull, !busy);
-                bool took_now = false;
                 if (q_rem > 0 && freeb != 0u) {
                     const int idx = q_next + __popc(freeb & ((1u << lane) - 1u));
                     if (!busy && idx < q_next + q_rem) {
                         const uint4 d = myq[idx];
                         if (!(d.w & 0x80u)) {
+                            const uint2 sg = myqs[idx];
                             i = q_base + idx; mypos = (int)d.y; r = __uint_as_float(d.z);
                             head = (uint32_t)i | ((d.w & 31u) << 24);
                             const int y = (int)d.x;
                             m2 = F.use_masks ? state_mask<ENV>(y, T.A, F.env_seed, full) : full;
                             if (m2 == 0u) atomicOr(T.err, kErrEmpty);  // np.max of an empty selection (QLO:764)
-                            const uint2 sg = __ldcg(X.seg + y);
                             p = sg.x; pe = sg.y;
                             const float* row = T.q + (size_t)y * T.ld;
 #pragma unroll
                             for (int c = 0; c < 2 * LPR; ++c) cp_async16(myrow + 4 * c, row + 4 * c);
-                            fresh = busy = took_now = true;
+                            fresh = busy = true;
                         }
                     }
                     const int took = min(__popc(freeb), q_rem);
                     q_next += took;
                     q_rem -= took;
                 }
-                if (busy && !took_now) {
+                if (busy) {
                     // ---- poll: the (up to four) records of the aligned 32-byte group at the cursor, in position (= agent) order
-                    bool go = true, fin = false;
-                    if (fresh) {
-                        cp_async_wait_all();
-                        fresh = false;
-                        FLOW_STAT(++st_fresh;)
-                        if (!(p < pe && pe <= (uint32_t)n)) p = pe = 0u;
-                        if (p >= pe) { fin = true; go = false; }  // nobody stands on s': the row is as the table has it
-                    }
+                    bool go = p < pe, fin = !go;  // nobody (left) on s': the row is as the replay has it
                     const uint32_t pa = p & ~3u;
                     FLOW_STAT(const uint32_t p0 = p;)
                     U8 e4;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) e4.w[j] = 0u;
                     if (go) e4 = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa));
+                    if (fresh) {
+                        cp_async_wait_all();
+                        fresh = false;
+                        FLOW_STAT(++st_fresh;)
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t ex = e4.w[2 * j], ey = e4.w[2 * j + 1];

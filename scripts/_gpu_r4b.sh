@@ -1,0 +1,11 @@
+export PYTHONPATH=$PWD
+echo "=== form tests"
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -q -x -k "all_forms or automatic" 2>&1 | tail -5
+echo "=== form 5 skip 40"
+QE_FORM=5 QE_SKIP=40 timeout 300 python scripts/perf_probe.py 1e6 16 1048576 8 3 2>&1 | tail -8
+echo "=== form 3 skip 40"
+QE_FORM=3 QE_SKIP=40 timeout 300 python scripts/perf_probe.py 1e6 16 1048576 8 3 2>&1 | tail -6
+echo "=== form 5 skip 256"
+QE_FORM=5 QE_SKIP=256 timeout 300 python scripts/perf_probe.py 1e6 16 1048576 8 3 2>&1 | tail -8
+echo "=== long test form 5"
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -q -x -k "long_run and 5" 2>&1 | tail -5
