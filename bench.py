@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hot path (masked eps-greedy select -> env step -> sequential TD update).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c1|c2|c4]
 
 One "step" = one vector step of all agents (N_agents agent-steps).  Metric: agent-steps/s (BASELINE.json).
 Workload at --gpus 1: BASELINE config 3 -- hash MDP, 1 000 000 states x 16 actions, 2^20 agents, masked actions,
@@ -45,7 +45,9 @@ WORKLOADS = {
     "c3": (1_000_000, 16, 1 << 20, "hash-MDP 1M states x 16 actions, 2^20 agents, masked (BASELINE config 3)"),
     "c4": (100_000_000, 8, 1 << 22, "hash-MDP 100M states x 8 actions, 2^22 agents, state-range sharded (BASELINE config 4)"),
     "c2": (19_683, 9, 128, "TicTacToe 19683 states x 9 actions, 128 agents, masked (BASELINE config 2)"),
+    "c1": (19_683, 9, 1, "TicTacToe 19683 states x 9 actions, 1 agent, masked (BASELINE config 1, the reference's own CPU-runnable case)"),
 }
+SMALL = ("c1", "c2")  # one-CTA kernel, TicTacToe
 EPS, LR, GAMMA, P_TERM, ENV_SEED, STREAM_SEED, TABLE_SEED = 0.1, 0.1, 0.99, 0.05, 0, 0, 1
 
 
@@ -185,7 +187,7 @@ def cpu_port_rate(workload: str, agents: int, steps: int, warm: int = 1):
     s, a, _n, _ = WORKLOADS[workload]
     thresh = np.full(max(steps, warm), orng.explore_threshold(EPS), dtype=np.uint64)
     lrs = np.full(max(steps, warm), LR, dtype=np.float32)
-    if workload == "c2":
+    if workload in SMALL:
         boards, states, masks = co.ttt_reset(orng.draw_uniforms(STREAM_SEED, T_INIT, 1, agents, 5)[0])
         q = np.zeros((s, a), dtype=np.float32)
         kind, env_state, slots, empty_all = co.ENV_TTT, boards, 5, False
@@ -210,7 +212,7 @@ def python_port_rate(workload: str, agents: int, steps: int):
     from oracle.envs import T_INIT, HashMDPVec, TicTacToeVec
 
     s, a, _n, _ = WORKLOADS[workload]
-    if workload == "c2":
+    if workload in SMALL:
         env, slots = TicTacToeVec(agents), 5
         q = np.zeros((s, a), dtype=np.float32)
     else:
@@ -237,8 +239,8 @@ class TwinEnv:
         from oracle.envs import HashMDPVec, TicTacToeVec
 
         s, a, _n, _ = WORKLOADS[workload]
-        self.inner = TicTacToeVec(agents) if workload == "c2" else HashMDPVec(agents, s, a, seed=ENV_SEED, p_term=P_TERM)
-        self.slots = 5 if workload == "c2" else 4
+        self.inner = TicTacToeVec(agents) if workload in SMALL else HashMDPVec(agents, s, a, seed=ENV_SEED, p_term=P_TERM)
+        self.slots = 5 if workload in SMALL else 4
         self.t = 0
         self.num_envs = agents
         self.agent0 = agent0
@@ -285,7 +287,7 @@ def reference_parallel_rates(workload: str, agents_per_env: int, steps_per_proc:
     out = {}
     for p in procs:
         algo = RefQL(s, a, GAMMA, seed=STREAM_SEED)
-        if workload != "c2":
+        if workload not in SMALL:
             algo.q_table = np.random.default_rng(TABLE_SEED).random((s, a))
         rt = RefParallel(algo, RefConstant(LR), RefConstant(EPS))
         envs = [TwinEnv(workload, agents_per_env, agent0=k * agents_per_env) for k in range(p)]
@@ -318,7 +320,7 @@ def cpu_baselines(workload: str, ref_steps: int = 4, quick: bool = False) -> dic
         out["single_thread"] = {"value": ref[0], "cores": 1, "sample": f"{ref_steps} vector steps x {ref_agents} agents ({ref[1]:.1f} s); {ref[2]}"}
         procs = sorted({p for p in (1, 2, 4, 8, cores) if p <= cores})
         per_env = min(n, 1 << 11)
-        spp = (50 if quick else 200) if workload == "c2" else (2 if quick else 8)
+        spp = (50 if quick else 200) if workload in SMALL else (2 if quick else 8)
         par = reference_parallel_rates(workload, per_env, spp, procs)
         out["multiprocessing"] = {"trainer": "unmodified reference ParallelQLearning.run_steps (one process per environment, shared-memory table, one lock around choose_actions and learn)",
                                   "agents_per_env": per_env, "vector_steps_per_process": spp, "by_processes": par,
@@ -329,12 +331,12 @@ def cpu_baselines(workload: str, ref_steps: int = 4, quick: bool = False) -> dic
             out["multiprocessing"]["best"] = {"value": best[0], "processes": best[1]}
     out["mpi"] = {"value": None, "status": "not runnable here: neither mpi4py nor an MPI launcher is installed (image and wheelhouse)",
                   "published_i7_11700K": {"8_ranks_128_agents": 76098, "2_ranks_128_agents": 22596, "source": "BASELINE.md (benchmark_results/distributed_128_agents_*_processes.json)"}}
-    cpu_agents = n if workload == "c2" else 1 << 20
-    cpu_steps = 2000 if workload == "c2" else (4 if quick else 12)
+    cpu_agents = n if workload in SMALL else 1 << 20
+    cpu_steps = 2000 if workload in SMALL else (4 if quick else 12)
     rate, dt = cpu_port_rate(workload if workload != "c4" else "c3", cpu_agents, cpu_steps)
     out["c_port"] = {"value": rate, "cores": cores, "sample": f"{cpu_steps} vector steps x {cpu_agents} agents, C port of the reference loop: OpenMP select + env step, sequential learn ({dt:.1f} s)"
                      + (" [config 3's table: config 4's 100M x 8 fp32 table is 3.2 GB per copy]" if workload == "c4" else "")}
-    py_agents, py_steps = (n, 50) if workload == "c2" else (1 << 13, 2 if quick else 4)
+    py_agents, py_steps = (n, 50) if workload in SMALL else (1 << 13, 2 if quick else 4)
     out["python_port"] = {"value": python_port_rate(workload if workload != "c4" else "c3", py_agents, py_steps), "cores": 1,
                           "sample": f"{py_steps} vector steps x {py_agents} agents, NumPy/Python restatement"}
     return out
@@ -363,7 +365,7 @@ def reference_rate(workload: str, agents: int, steps: int, warm: int = 1):
             return None
 
     algo = RefQL(s, a, GAMMA, seed=STREAM_SEED)
-    if workload != "c2":
+    if workload not in SMALL:
         algo.q_table = np.random.default_rng(TABLE_SEED).random((s, a))
     rt = Loop(algo, RefConstant(LR), RefConstant(EPS))
     env = TwinEnv(workload, agents)
@@ -549,7 +551,7 @@ def run_ours(args) -> dict | None:
     lib = capi.lib()
     K, W = args.steps, max(3, args.warmup)  # (at least three warm-up steps; the first launch also pays for module loading)
     # 128 TicTacToe agents take ~11 us per vector step: only long launches amortise the ~40 us a launch costs
-    per_launch = 256 if (workload == "c2" and world == 1) else SYNC_EVERY
+    per_launch = 256 if (workload in SMALL and world == 1) else SYNC_EVERY
     stream = torch.cuda.current_stream()
 
     def sync_all():
@@ -574,7 +576,7 @@ def run_ours(args) -> dict | None:
 
     def make():
         algo = OptimalQLearningBase(s, a, GAMMA, seed=STREAM_SEED, device=local)
-        if workload == "c2":
+        if workload in SMALL:
             env = TicTacToeVecEnv(n, seed=STREAM_SEED, device=local, output="torch")
         else:
             algo.fill_random(TABLE_SEED)
@@ -699,7 +701,7 @@ def run_ours(args) -> dict | None:
     # of steps 256..288.
     late = None
     value_long = None
-    if world == 1 and workload != "c2" and not args.no_late:
+    if world == 1 and workload not in SMALL and not args.no_late:
         del algo, env
         algo, env = make()
         ep_ret = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -762,7 +764,7 @@ def run_ours(args) -> dict | None:
         peak_gbs = measured_peak()[0]
         atomics = {"td_update": "learn_vec semantics: snapshot bootstrap + atomicAdd scatter (not what the reference's trainers call)",
                    "value": n / (acc_ms * 1e-3), "unit": "agent-steps/s", "steps": K, "ms_per_step": acc_ms, "phase_us_per_step": acc_phases,
-                   "roofline_frac": n * alg_bytes(a) / (acc_ms * 1e-3) / 1e9 / peak_gbs, "kernel": "fused_kernel<MDP,2,ACC>" if workload != "c2" else "fused_kernel<TTT,2,ACC>"}
+                   "roofline_frac": n * alg_bytes(a) / (acc_ms * 1e-3) / 1e9 / peak_gbs, "kernel": "fused_kernel<MDP,2,ACC>" if workload not in SMALL else "fused_kernel<TTT,2,ACC>"}
         del algo, env
 
     # ---------------- e2e through the public API: per step H2D of that step's uniforms (pinned) + D2H of the results
@@ -772,7 +774,7 @@ def run_ours(args) -> dict | None:
     runner = D.ReplicatedQLearning(rt, tp, sync_every=SYNC_EVERY, carry_over=True) if tp is not None else rt
     # config 2's 128 agents take ~10 us per vector step: one host round trip per step would measure the host.  The caller
     # asks for 64 steps per call there (their uniforms go down in one copy, their results come back once), one elsewhere.
-    call_steps = 64 if (workload == "c2" and world == 1) else 1
+    call_steps = 64 if (workload in SMALL and world == 1) else 1
     Ke = (min(K, 2048) // call_steps) * call_steps if call_steps > 1 else min(K, 20)
     Ke = max(Ke, call_steps)
     We = max(call_steps, min(W, 4 * call_steps)) if call_steps > 1 else W
@@ -882,7 +884,7 @@ def run_ours(args) -> dict | None:
                 traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:  # noqa: BLE001
             traffic = None
-    kname = FORM_KERNELS.get(form_id, "fused_kernel") + (("<TTT>" if form_id == 4 else "<TTT,2>") if workload == "c2" else ("<MDP,1>" if a <= 8 else "<MDP,2>"))
+    kname = FORM_KERNELS.get(form_id, "fused_kernel") + (("<TTT>" if form_id == 4 else "<TTT,2>") if workload in SMALL else ("<MDP,1>" if a <= 8 else "<MDP,2>"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_agent_step": balg,
                 "algorithmic_bytes_per_launch": n * steps_per_launch * balg, "avg_launch_ms": per_launch_ms,
@@ -900,7 +902,7 @@ def run_ours(args) -> dict | None:
                             "sample": base["c_port"]["sample"], **{k: v for k, v in base.items() if k != "c_port"}}
     cfg = {"workload": f"{workload}: {desc}" + (f", one replica per GPU, Q-delta all-reduce every {SYNC_EVERY} steps (BASELINE config 5)" if world > 1 else ""),
            "states": s, "actions": a, "agents_per_gpu": n, "agents": n * world, "eps": EPS, "lr": LR, "gamma": GAMMA, "p_term": P_TERM,
-           "table_init": "uniform[0,1)" if workload != "c2" else "zeros", "rng": "on-device counter stream",
+           "table_init": "uniform[0,1)" if workload not in SMALL else "zeros", "rng": "on-device counter stream",
            "steps_per_launch": per_launch,
            "timing": "CUDA events around the K timed steps (max over ranks); no L2 flush: every vector step touches the dense table (64 MB at "
                      "config 3) plus ~90 MB of per-agent / per-position arrays, more than the 126 MB L2 (ncu: L2 hit rate 65 %)",

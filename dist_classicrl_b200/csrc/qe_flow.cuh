@@ -306,53 +306,74 @@ __device__ __forceinline__ void flow_warp_pass(int* cnt, const int2* src, int2* 
     __syncwarp();
 }
 
-// ---- one warp, one bucket, one pass (the low bits are one digit): the bucket is staged in shared memory first, so global
-// memory is read once with every load in flight and the counting / ranking loops run out of shared memory.
-__device__ __forceinline__ void flow_warp_staged(int* cnt, int2* stage, uint16_t* order, const int2* src, int2* dst, int lo, int hi, int bits,
-                                                 int32_t key_hi, const FlowScratch& X) {
+// ---- TWO warps, one bucket, one pass: as flow_warp_staged, the bucket split in halves.  A bucket sort is one long chain of
+// dependent instructions (count, scan, rank, write: ~50 cycles per element for a single warp), so a second warp nearly
+// halves it.  Stable: the first warp's half precedes the second's within every digit (own counters per warp, the scan
+// gives the second warp's elements of a digit the places behind the first's).  The team meets at a named barrier.
+__device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void flow_team_staged(int tw, int bar_id, int* cnt2, int* s_tot, uint32_t* sagent, uint16_t* sdigit, uint16_t* order,
+                                                 const int2* src, int2* dst, int lo, int hi, int bits, int32_t key_hi, const FlowScratch& X) {
     const int lane = threadIdx.x & 31;
     const int nd = 1 << bits, m = hi - lo;
     const uint32_t dm = (uint32_t)nd - 1u;
+    const int h = min(((m + 63) >> 6) << 5, m);          // the first warp's share (whole groups of 32)
+    const int x0 = tw ? h : 0, x1 = tw ? m : h;
+    int* cnt = cnt2 + tw * kRadix;                         // this warp's counters; the other's: cnt2 + (tw ^ 1) * kRadix
     for (int d = lane; d < nd; d += 32) cnt[d] = 0;
-    for (int base = 0; base < m; base += 256) {
+    for (int base = x0; base < x1; base += 256) {
         int2 e[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) e[u] = base + 32 * u + lane < m ? __ldcg(src + lo + base + 32 * u + lane) : make_int2(0, 0);
+        for (int u = 0; u < 8; ++u) e[u] = base + 32 * u + lane < x1 ? __ldcg(src + lo + base + 32 * u + lane) : make_int2(0, 0);
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (base + 32 * u + lane < m) stage[base + 32 * u + lane] = e[u];
+            if (base + 32 * u + lane < x1) {
+                sagent[base + 32 * u + lane] = (uint32_t)e[u].y;
+                sdigit[base + 32 * u + lane] = (uint16_t)((uint32_t)e[u].x & dm);
+            }
     }
     __syncwarp();
-    for (int x = lane; x < m; x += 32) smem_inc(&cnt[(uint32_t)stage[x].x & dm]);
-    __syncwarp();
-    int run = 0;
-    for (int j = 0; j < nd; j += 32) {  // exclusive scan in digit order (digit j + lane); a digit is a state: its bounds
-        const int d = j + lane;
-        const int v = d < nd ? cnt[d] : 0;
+    for (int x = x0 + lane; x < x1; x += 32) smem_inc(&cnt[sdigit[x]]);
+    team_bar(bar_id);
+    // exclusive scan in digit order: this warp does the digits [tw * nd / 2, ...); a digit is a state: its bounds
+    const int* c0 = cnt2;
+    const int* c1 = cnt2 + kRadix;
+    const int dh = nd >> 1, d0 = tw ? dh : 0, d1 = tw ? nd : dh;
+    {
+        int part = 0;
+        for (int d = d0 + lane; d < d1; d += 32) part += c0[d] + c1[d];
+        part = __reduce_add_sync(kFull, part);
+        if (lane == 0) s_tot[tw] = part;
+    }
+    team_bar(bar_id);
+    int run = tw ? s_tot[0] : 0;
+    for (int j = 0; j < dh; j += 32) {  // (a warp reads and rewrites the counters of its own digits only)
+        const int d = d0 + j + lane;
+        const bool in = d < d1;
+        const int va = in ? c0[d] : 0, vb = in ? c1[d] : 0, v = va + vb;
         const int incl = warp_incl_scan(v);
         const int first = run + incl - v;
-        if (d < nd) cnt[d] = first;
+        if (in) { cnt2[d] = first; cnt2[kRadix + d] = first + va; }
         if (v > 0) X.seg[key_hi | d] = make_uint2((uint32_t)(lo + first), (uint32_t)(lo + first + v));
         run += __shfl_sync(kFull, incl, 31);
     }
-    __syncwarp();
-    // ranks in shared memory (order[rank] = where the element sits in the staging area) ...
-    for (int base = 0; base < m; base += 32) {
-        const bool act = base + lane < m;
-        const uint32_t d = act ? ((uint32_t)stage[base + lane].x & dm) : 0u;
+    team_bar(bar_id);
+    for (int base = x0; base < x1; base += 32) {
+        const bool act = base + lane < x1;
+        const uint32_t d = act ? (uint32_t)sdigit[base + lane] : 0u;
         const uint32_t peers = digit_peers(d, act);
         if (act) order[cnt[d] + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)(base + lane);
         __syncwarp();
         if (act && lane == (__ffs(peers) - 1)) cnt[d] += __popc(peers);
         __syncwarp();
     }
-    // ... so that the finished order and the fresh writer records leave as whole lines; only agent -> position is scattered
-    for (int x = lane; x < m; x += 32) {
-        const int2 e = stage[order[x]];
+    team_bar(bar_id);
+    for (int x = lane + 32 * tw; x < m; x += 64) {  // (only agent -> position is scattered)
+        const int o = order[x];
+        const uint32_t ag = sagent[o];
         const int q = lo + x;
-        dst[q] = e;
-        X.rec[q] = (uint64_t)(uint32_t)e.y;
-        X.pos[e.y] = q;
+        dst[q] = make_int2(key_hi | (int32_t)sdigit[o], (int32_t)ag);
+        X.rec[q] = (uint64_t)ag;
+        X.pos[ag] = q;
     }
 }
 
@@ -366,35 +387,29 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
     const int L = X.local_passes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x, nb = gridDim.x;
-    // at most three buckets per block (the usual grid): warps 0..2 own one each and a third of the arena (counters + staging area)
+    // at most three buckets per block (the usual grid): a TEAM of two warps (2|3, 4|5, 6|7; warps 0 and 1 stay out -- warp
+    // 0 runs several times slower here) owns one and a third of the arena (two sets of counters + staging area)
     const bool slots = (kRadix - 1) / nb < 3;
     const int slot_bytes = (arena_bytes / 3) & ~15;
-    const int stage_cap = min(((slot_bytes - (int)sizeof(int) * kRadix) / (int)(sizeof(int2) + sizeof(uint16_t))) & ~7, 65535);
-    const int wsh = slots ? ((X.flags & 2) ? 0 : 4) : 0;  // warps 4..6 own the buckets (warp 0 runs several times slower here; QE_FLOW_FLAGS=2: warps 0..2)
-    const int ow = warp - wsh;                                                            // owner index of this warp (0..2 own buckets)
-    int* cnt = slots ? reinterpret_cast<int*>(arena + (size_t)((ow >= 0 && ow < 3) ? ow : 0) * slot_bytes) : whist[warp];
-    int2* stage = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(cnt) + sizeof(int) * kRadix);
-    uint16_t* order = reinterpret_cast<uint16_t*>(stage + stage_cap);
+    const int team = slots ? (warp >= 2 ? (warp - 2) >> 1 : -1) : 0, tw = slots ? (warp & 1) : 0;
+    int* cnt = slots ? reinterpret_cast<int*>(arena + (size_t)(team >= 0 ? team : 0) * slot_bytes) : whist[warp];
+    const int stage_cap = min(((slot_bytes - 2 * (int)sizeof(int) * kRadix - 16) / 8) & ~7, 65535);
+    int* s_tot = cnt + 2 * kRadix;  // [2] (+ 2 words of padding)
+    uint32_t* sagent = reinterpret_cast<uint32_t*>(s_tot + 4);
+    uint16_t* sdigit = reinterpret_cast<uint16_t*>(sagent + stage_cap);
+    uint16_t* order = sdigit + stage_cap;
     bool big = false;
-    for (int j = slots ? (ow >= 0 ? ow : WARPS * kRadix) : warp; j * nb + b < kRadix; j += WARPS) {
+    for (int j = slots ? (team >= 0 ? team : WARPS * kRadix) : warp; j * nb + b < kRadix; j += WARPS) {
         const int d = j * nb + b;
         const int lo = s_base[d], hi = s_base[d + 1];
         if (hi <= lo) continue;
         if (hi - lo > kWarpBucketMax) { big = true; continue; }
-        if (L == 1 && slots && hi - lo <= stage_cap && !(X.flags & 1)) {
-            const uint64_t t0 = global_ns();
-            flow_warp_staged(cnt, stage, order, X.kv[1], X.kv[0], lo, hi, X.msd_shift, (int32_t)((uint32_t)d << X.msd_shift), X);
-            if (lane == 0) {
-                const unsigned int dt = (unsigned int)((global_ns() - t0) >> 6);
-                atomicMax(X.ctr + 8, (dt << 13) | (unsigned int)min(hi - lo, 8191));  // slowest bucket: {ns / 64, size}
-                atomicMax(X.ctr + 11, (dt << 10) | (unsigned int)d);
-                atomicAdd(X.ctr + 16 + min(dt >> 7, 15u), 1u);                      // histogram, 8 us bins
-                if ((dt >> 7) >= 6u) { atomicAdd(X.ctr + 32 + warp, 1u); atomicAdd(X.ctr + 40 + (b * 8) / nb, 1u); atomicAdd(X.ctr + 48 + min((hi - lo) >> 8, 7), 1u); }
-                else atomicAdd(X.ctr + 56 + min((hi - lo) >> 8, 7), 1u);
-            }
+        if (L == 1 && slots && hi - lo <= stage_cap && !(X.flags & 1)) {  // (the same answer in both warps of the team)
+            flow_team_staged(tw, 1 + team, cnt, s_tot, sagent, sdigit, order, X.kv[1], X.kv[0], lo, hi, X.msd_shift,
+                             (int32_t)((uint32_t)d << X.msd_shift), X);
             continue;
         }
-        const uint64_t t0 = global_ns();
+        if (slots && tw) continue;  // everything else: one warp per bucket
         int src = L & 1;
         for (int ps = 0; ps < L; ++ps) {
             const int shift = ps * kRadixBits;
@@ -418,7 +433,6 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
                 if (next != k) X.seg[k].y = (uint32_t)(q + 1);
             }
         }
-        if (lane == 0) atomicMax(X.ctr + 9, (unsigned int)(((global_ns() - t0) >> 6) << 13) | (unsigned int)min(hi - lo, 8191));
     }
     if (!__syncthreads_or(big)) return;
     if (threadIdx.x == 0) atomicAdd(X.ctr + 10, 1u);  // blocks with a large bucket
@@ -444,9 +458,11 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
     }
 }
 
+constexpr size_t kFlowExtraBytes = 8192;  // more staging room for the bucket sorts (herded buckets of up to ~1800 agents stay on the fast path)
 __host__ __device__ constexpr int flow_row_words(int lpr) { return 8 * lpr + 4; }  // one replayed row per thread, 16-byte aligned, conflict-free
 __host__ __device__ constexpr size_t flow_smem_bytes(int lpr) {
-    return sizeof(int) * ((size_t)8 * kRadix + kRadix + 8) + (sizeof(uint4) + sizeof(uint2)) * 8 * 32 + sizeof(float) * (size_t)flow_row_words(lpr) * 256;
+    return sizeof(int) * ((size_t)8 * kRadix + kRadix + 8) + (sizeof(uint4) + sizeof(uint2)) * 8 * 32 + sizeof(float) * (size_t)flow_row_words(lpr) * 256 +
+           kFlowExtraBytes;
 }
 #ifndef QE_FLOW_MIN_BLOCKS
 #define QE_FLOW_MIN_BLOCKS 3
@@ -765,31 +781,84 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
         // records, tiles claimed dynamically; a segment's row lives in the shared-memory column of its head lane, the
         // members take turns in position (= agent) order; what extends beyond the tile is replayed by the whole warp, one
         // lane per action.  The bounds of the segment are cleared on the way (the bucket sorts write the next ones).
+        // The loop is software-pipelined, because a tile is a chain of three round trips (claim, records, rows) and little
+        // else: while tile A is applied, the rows of tile B and the records of tile C are on their way and the claim of the
+        // pair after that is in flight.  A warp's first pair is its own index (no 3552-way rush on the counter).
         flow_scan<WARPS>(X);
+        {
+            const int nw2 = 2 * gridDim.x * WARPS;
+            auto claim_raw2 = [&]() {
+                int c = 0;
+                if (lane == 0) c = (int)atomicAdd(X.ctr + 2, 2u);
+                return c;
+            };
+            int nx_tile = 2 * (blockIdx.x * WARPS + warp), nx_left = 2;
+            int nx_pair = nw2 + __shfl_sync(kFull, claim_raw2(), 0);
+            int raw = claim_raw2();
+            auto next_tile = [&]() {
+                if (nx_left == 0) {
+                    nx_tile = nx_pair;
+                    nx_left = 2;
+                    nx_pair = nw2 + __shfl_sync(kFull, raw, 0);
+                    raw = claim_raw2();
+                }
+                --nx_left;
+                return nx_tile++;
+            };
+            struct TileIn { int tile; uint64_t e; uint32_t st, pv; uint64_t e2; uint32_t k2; };  // e2 / k2: the same lane of the following tile
+            auto load_in = [&](int tile) {
+                TileIn t{tile, 0ull, 0xFFFFFFFFu, 0xFFFFFFFFu, 0ull, 0xFFFFFFFFu};
+                const int p = tile * 32 + lane;
+                if (tile < ntiles && p < n) { t.e = __ldcg(rec + p); t.st = (uint32_t)__ldcg(&sorted[p].x); }
+                if (tile < ntiles && p + 32 < n) { t.e2 = __ldcg(rec + p + 32); t.k2 = (uint32_t)__ldcg(&sorted[p + 32].x); }
+                if (tile < ntiles && lane == 0 && p > 0) t.pv = (uint32_t)__ldcg(&sorted[p - 1].x);
+                return t;
+            };
+            auto is_head = [&](const TileIn& t) {
+                const int p = t.tile * 32 + lane;
+                uint32_t prev = __shfl_up_sync(kFull, t.st, 1);
+                if (lane == 0) prev = t.pv;
+                return t.tile < ntiles && p < n && (p == 0 || prev != t.st);
+            };
+            struct TileRows { F8 v[LPR]; };
+            auto load_rows = [&](const TileIn& t) {
+                TileRows r;
+                const bool head = is_head(t);
+                const float* row = T.q + (size_t)(head ? t.st : 0u) * T.ld;
+#pragma unroll
+                for (int c = 0; c < LPR; ++c) {
+                    if (head) r.v[c] = ld_row8(row + 8 * c);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) r.v[c].v[j] = 0.0f;
+                    }
+                }
+                return r;
+            };
+            TileIn tA = load_in(next_tile());
+            TileIn tB = load_in(next_tile());
+            TileRows rA = load_rows(tA);
         for (;;) {
-            int tile = 0;
-            if (lane == 0) tile = (int)atomicAdd(X.ctr + 2, 2u);
-            tile = __shfl_sync(kFull, tile, 0);
-            if (tile >= ntiles) break;
-            for (const int tend = min(tile + 2, ntiles); tile < tend; ++tile) {
+            if (tA.tile >= ntiles) break;  // (the tiles of a warp increase)
+            const TileRows rB = load_rows(tB);
+            const TileIn tC = load_in(next_tile());
+            {
+                const int tile = tA.tile;
                 const int p = tile * 32 + lane;
                 const bool act = p < n;
-                uint64_t e = 0ull;
-                uint32_t st = 0xFFFFFFFFu;  // state of this position
-                if (act) { e = __ldcg(rec + p); st = (uint32_t)__ldcg(&sorted[p].x); }
+                const uint64_t e = tA.e;
+                const uint32_t st = tA.st;  // state of this position
                 const uint32_t ex = (uint32_t)e, ey = (uint32_t)(e >> 32);
-                uint32_t prev = __shfl_up_sync(kFull, st, 1);
-                if (lane == 0) prev = p > 0 ? (uint32_t)__ldcg(&sorted[p - 1].x) : 0xFFFFFFFFu;
-                const bool head = act && (p == 0 || prev != st);
+                const bool head = is_head(tA);
                 const uint32_t hb = __ballot_sync(kFull, head);
                 const uint32_t below = hb & (0xFFFFFFFFu >> (31 - lane));
                 const int hl = below ? 31 - __clz(below) : -1;  // head lane of this lane's segment; -1: the segment began in an earlier tile
                 if (act && !(ex & kRecFinal)) atomicOr(T.err, kErrTimeout);  // cannot happen: the in-order pass published every target
                 if (head) {
-                    const float* row = T.q + (size_t)st * T.ld;
 #pragma unroll
                     for (int c = 0; c < LPR; ++c) {
-                        const F8 v8 = ld_row8(row + 8 * c);
+                        const F8 v8 = rA.v[c];
+
 #pragma unroll
                         for (int j = 0; j < 8; ++j) s_row[(8 * c + j) * 256 + threadIdx.x] = v8.v[j];
                     }
@@ -817,9 +886,13 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                     float v = lane < 8 * LPR ? s_row[lane * 256 + c] : 0.0f;
                     bool touched = false;
                     for (int q = tile * 32 + 32; q < n; q += 32) {
-                        uint64_t e2 = 0ull;
-                        uint32_t k2 = 0xFFFFFFFFu;
-                        if (q + lane < n) { e2 = __ldcg(rec + q + lane); k2 = (uint32_t)__ldcg(&sorted[q + lane].x); }
+                        uint64_t e2 = tA.e2;  // (the following tile came with this one: two out of three tiles need it)
+                        uint32_t k2 = tA.k2;
+                        if (q > tile * 32 + 32) {
+                            e2 = 0ull;
+                            k2 = 0xFFFFFFFFu;
+                            if (q + lane < n) { e2 = __ldcg(rec + q + lane); k2 = (uint32_t)__ldcg(&sorted[q + lane].x); }
+                        }
                         const uint32_t diff = __ballot_sync(kFull, k2 != st31);
                         const int len = diff ? __ffs(diff) - 1 : 32;
                         for (int j = 0; j < len; ++j) {
@@ -843,6 +916,10 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                 }
                 __syncwarp();
             }
+            tA = tB;
+            tB = tC;
+            rA = rB;
+        }
         }
         grid.sync();
         if (clk && k < 10) F.phase_ns[2 + 3 * k] = global_ns();
