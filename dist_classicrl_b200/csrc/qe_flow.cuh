@@ -104,9 +104,10 @@ template <int WARPS>
 __device__ __forceinline__ void flow_scan(const FlowScratch& X) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nb = gridDim.x;
-    const int gw = blockIdx.x * WARPS + warp, nw = nb * WARPS;
     const int per = (nb + 31) / 32;
-    for (int d = gw; d < kRadix; d += nw) {
+    // bucket d belongs to warp d / nb of block d % nb: one to three warps per block scan a row each while the block's other
+    // warps go on to the commit (all rows on the first kRadix / WARPS blocks: those blocks reach the commit ~10 us late)
+    for (int d = blockIdx.x + warp * nb; d < kRadix; d += WARPS * nb) {
         int* row = X.ghist + (size_t)d * nb;
         int v[kScanPerLane];
         int sum = 0;
@@ -458,12 +459,15 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
     }
 }
 
-constexpr size_t kFlowExtraBytes = 8192;  // more staging room for the bucket sorts (herded buckets of up to ~1800 agents stay on the fast path)
+constexpr size_t kFlowExtraBytes = 0;  // (3 x 63.5 KB fit the 196 KB shared-memory carve-out; one step more and the L1 shrinks: scatter +2 us, in-order pass +3 us)
 __host__ __device__ constexpr int flow_row_words(int lpr) { return 8 * lpr + 4; }  // one replayed row per thread, 16-byte aligned, conflict-free
 __host__ __device__ constexpr size_t flow_smem_bytes(int lpr) {
     return sizeof(int) * ((size_t)8 * kRadix + kRadix + 8) + (sizeof(uint4) + sizeof(uint2)) * 8 * 32 + sizeof(float) * (size_t)flow_row_words(lpr) * 256 +
            kFlowExtraBytes;
 }
+#ifndef QE_FLOW_CLAIM
+#define QE_FLOW_CLAIM 2
+#endif
 #ifndef QE_FLOW_MIN_BLOCKS
 #define QE_FLOW_MIN_BLOCKS 3
 #endif
@@ -539,13 +543,26 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
         {
             unsigned int* claim = X.ctr;
             float* myrow = s_rows + threadIdx.x * RS;
-            auto claim_raw = [&]() {  // lane 0's answer; nobody waits for it before claim_get
+            // chunks are claimed kClaim at a time (ONE counter serves the whole grid; same-address atomics are ~2 ns apiece) and
+            // the claim after the current one is always in flight: nobody waits for the counter's round trip
+            constexpr int kClaim = QE_FLOW_CLAIM;
+            auto claim_raw = [&]() {  // lane 0's answer; nobody waits for it before it is needed
                 int c = 0;
-                if (lane == 0) c = (int)atomicAdd(claim, 1u);
+                if (lane == 0) c = (int)atomicAdd(claim, (unsigned int)kClaim);
                 return c;
             };
-            auto claim_get = [&](int c) { return __shfl_sync(kFull, c, 0) * 32; };
-            auto claim_chunk = [&]() { return claim_get(claim_raw()); };
+            int ch_next = 0, ch_left = 0, ch_raw = claim_raw();
+            auto next_chunk = [&]() {  // first agent of the warp's next chunk (>= n: no more)
+                if (ch_left == 0) {
+                    ch_next = __shfl_sync(kFull, ch_raw, 0) * 32;
+                    ch_left = kClaim;
+                    ch_raw = claim_raw();
+                }
+                --ch_left;
+                const int c = ch_next;
+                ch_next += 32;
+                return c;
+            };
             uint32_t m2 = 0u;  // legal actions of the row this lane is replaying (illegal cells never reach the max)
             auto row_max = [&]() {
                 float m = -INFINITY;
@@ -566,12 +583,11 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
             // lane, not a chunk.
             uint4* myq = s_queue + warp * 32;  // {next state, sorted position, reward bits, action | done << 7}
             uint2* myqs = s_qseg + warp * 32;  // {start, end} of the segment of the next state
-            int cb = ((X.flags & 8) && warp == 0) ? n : claim_chunk();  // (development: warp 0 sits the pass out)
+            int cb = next_chunk();
             int s_nx = 0, pos_nx = 0;
             float ep_nx = 0.0f;
             if (cb + lane < n) { s_nx = cur[cb + lane]; pos_nx = X.pos[cb + lane]; ep_nx = F.ep_ret[cb + lane]; }
-            int cbn = cb >= n ? n : claim_chunk();
-            int cbnn_raw = cb >= n ? (n >> 5) + 1 : claim_raw();  // (two claims ahead, the second one still in flight: the counter's round trip stays off the critical path)
+            int cbn = cb >= n ? n : next_chunk();
             const uint64_t t_start = global_ns();
             if (cb >= n && lane == 0) atomicAdd(X.ctr + 1, 1u);  // a warp without work: its "all my chunks are stepped" arrival
             int q_base = 0, q_next = 0, q_rem = 0;
@@ -657,8 +673,7 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                     if (cbn >= n && lane == 0) { __threadfence(); atomicAdd(X.ctr + 1, 1u); }
                     q_base = cb; q_next = 0; q_rem = min(32, n - cb);
                     cb = cbn;
-                    cbn = claim_get(cbnn_raw);
-                    cbnn_raw = claim_raw();
+                    cbn = next_chunk();
                 }
                 // ---- consume: the free lanes take the next agents of the queue, in order.  The bootstrap row travels to the
                 // lane's shared-memory slot asynchronously (cp.async, no registers) beside the first poll of the writer records
@@ -786,19 +801,20 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
         // pair after that is in flight.  A warp's first pair is its own index (no 3552-way rush on the counter).
         flow_scan<WARPS>(X);
         {
-            const int nw2 = 2 * gridDim.x * WARPS;
+            constexpr int kGroup = 2;  // tiles per claim (8 per claim: 40 us instead of 31 -- tiles differ a lot in cost, small claims balance them)
+            const int nw2 = kGroup * gridDim.x * WARPS;
             auto claim_raw2 = [&]() {
                 int c = 0;
-                if (lane == 0) c = (int)atomicAdd(X.ctr + 2, 2u);
+                if (lane == 0) c = (int)atomicAdd(X.ctr + 2, (unsigned int)kGroup);
                 return c;
             };
-            int nx_tile = 2 * (blockIdx.x * WARPS + warp), nx_left = 2;
+            int nx_tile = kGroup * (blockIdx.x * WARPS + warp), nx_left = kGroup;
             int nx_pair = nw2 + __shfl_sync(kFull, claim_raw2(), 0);
             int raw = claim_raw2();
             auto next_tile = [&]() {
                 if (nx_left == 0) {
                     nx_tile = nx_pair;
-                    nx_left = 2;
+                    nx_left = kGroup;
                     nx_pair = nw2 + __shfl_sync(kFull, raw, 0);
                     raw = claim_raw2();
                 }
