@@ -254,59 +254,6 @@ __device__ __forceinline__ void flow_local_pass(int (*whist)[kRadix], int* s_wsu
     __syncthreads();
 }
 
-// ---- one warp, one bucket: stable counting pass over [lo, hi) of src -> dst with the warp's own counters (no block
-// barrier).  The LAST pass also writes position and fresh writer record of every element, and -- when it is the only
-// pass, so that a digit IS a state of the bucket -- the segment bounds straight from the digit counts.
-__device__ __forceinline__ void flow_warp_pass(int* cnt, const int2* src, int2* dst, int lo, int hi, int shift, int bits, bool last,
-                                               bool bounds, int32_t key_hi, const FlowScratch& X) {
-    const int lane = threadIdx.x & 31;
-    const int nd = 1 << bits;
-    const uint32_t dm = (uint32_t)nd - 1u;
-    for (int d = lane; d < nd; d += 32) cnt[d] = 0;
-    __syncwarp();
-    for (int base = lo; base < hi; base += 256) {  // eight loads in flight per lane
-        int32_t kk[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) kk[u] = base + 32 * u + lane < hi ? __ldcg(&src[base + 32 * u + lane].x) : 0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (base + 32 * u + lane < hi) smem_inc(&cnt[((uint32_t)kk[u] >> shift) & dm]);
-    }
-    __syncwarp();
-    int run = lo;
-    for (int j = 0; j < nd; j += 32) {  // exclusive scan in digit order, digit j + lane
-        const int d = j + lane;
-        const int v = d < nd ? cnt[d] : 0;
-        const int incl = warp_incl_scan(v);
-        const int first = run + incl - v;
-        if (d < nd) cnt[d] = first;
-        if (bounds && v > 0) X.seg[key_hi | d] = make_uint2((uint32_t)first, (uint32_t)(first + v));
-        run += __shfl_sync(kFull, incl, 31);
-    }
-    __syncwarp();
-    for (int base = lo; base < hi; base += 256) {
-        int2 e[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) e[u] = base + 32 * u + lane < hi ? __ldcg(src + base + 32 * u + lane) : make_int2(0, 0);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (base + 32 * u >= hi) break;  // (uniform)
-            const bool act = base + 32 * u + lane < hi;
-            const uint32_t d = ((uint32_t)e[u].x >> shift) & dm;
-            const uint32_t peers = digit_peers(d, act);
-            if (act) {
-                const int q = cnt[d] + __popc(peers & ((1u << lane) - 1u));
-                dst[q] = e[u];
-                if (last) { X.pos[e[u].y] = q; X.rec[q] = (uint64_t)(uint32_t)e[u].y; }
-            }
-            __syncwarp();
-            if (act && lane == (__ffs(peers) - 1)) cnt[d] += __popc(peers);
-            __syncwarp();
-        }
-    }
-    __syncwarp();
-}
-
 // ---- TWO warps, one bucket, one pass: as flow_warp_staged, the bucket split in halves.  A bucket sort is one long chain of
 // dependent instructions (count, scan, rank, write: ~50 cycles per element for a single warp), so a second warp nearly
 // halves it.  Stable: the first warp's half precedes the second's within every digit (own counters per warp, the scan
@@ -378,9 +325,114 @@ __device__ __forceinline__ void flow_team_staged(int tw, int bar_id, int* cnt2, 
     }
 }
 
-// ---- the buckets of this block: sort by the low bits, then positions, segment bounds and fresh writer records.  A
-// bucket of ordinary size belongs to ONE warp (all buckets of the grid are in flight at once, no block barriers);
-// the few that herding makes large are done afterwards by the whole block.
+// ---- the WHOLE block, one bucket whose low `bits` bits are still unsorted (several digits: large tables; or a bucket that
+// herding made too large for a team): LSD passes of 8 bits entirely in shared memory.  Staged: the low bits of every key
+// (4 bytes) and two permutations (2 bytes each) -- the agents stay in global memory and are gathered once, at the end.
+// emit(position, state, agent) files one element of the finished order; the bounds come from the neighbours.
+constexpr int kBlockDigitBits = 8;
+__device__ __forceinline__ uint32_t digit_peers_bits(uint32_t d, bool act, int nbits) {
+    uint32_t peers = __ballot_sync(kFull, act);
+    for (int bit = 0; bit < nbits; ++bit) {
+        const bool one = (d >> bit) & 1u;
+        const uint32_t bb = __ballot_sync(kFull, one);
+        peers &= one ? bb : ~bb;
+    }
+    return peers;
+}
+__host__ __device__ constexpr int flow_block_cap(int arena_bytes) {
+    return ((arena_bytes - 8 * (1 << kBlockDigitBits) * (int)sizeof(int)) / 8) & ~31;
+}
+template <int WARPS, class Emit>
+__device__ __forceinline__ void flow_block_staged(unsigned char* arena, int arena_bytes, int* s_wsum, const int2* src, int lo, int hi, int bits,
+                                                  int32_t key_hi, uint2* seg, Emit emit) {
+    constexpr int ND = 1 << kBlockDigitBits;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = hi - lo, cap = min(flow_block_cap(arena_bytes), 65535);
+    int (*wc)[ND] = reinterpret_cast<int (*)[ND]>(arena);                       // [WARPS][ND] per-warp digit counters
+    uint32_t* key = reinterpret_cast<uint32_t*>(arena + sizeof(int) * WARPS * ND);  // [cap] low bits of the keys, by arrival
+    uint16_t* oa = reinterpret_cast<uint16_t*>(key + cap);                          // [cap] permutations (ping-pong)
+    uint16_t* ob = oa + cap;
+    const uint32_t mask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+    for (int x0 = 0; x0 < m; x0 += 4 * 256) {  // four loads in flight per thread
+        int32_t kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kk[u] = x0 + 256 * u + (int)threadIdx.x < m ? __ldcg(&src[lo + x0 + 256 * u + threadIdx.x].x) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (x0 + 256 * u + (int)threadIdx.x < m) key[x0 + 256 * u + threadIdx.x] = (uint32_t)kk[u] & mask;
+    }
+    const int tiles = (m + 31) >> 5;
+    const int pw = tiles / WARPS, rw = tiles % WARPS;
+    const int t0 = warp * pw + min(warp, rw), t1 = t0 + pw + (warp < rw ? 1 : 0);
+    const int w0 = min(t0 * 32, m), w1 = min(t1 * 32, m);  // this warp's slice of the current order
+    uint16_t* cur = oa;
+    uint16_t* nxt = ob;
+    const int P = (bits + kBlockDigitBits - 1) / kBlockDigitBits;
+    __syncthreads();
+    for (int ps = 0; ps < P; ++ps) {
+        const int shift = ps * kBlockDigitBits, nb_bits = min(kBlockDigitBits, bits - shift);
+        const uint32_t dm = (1u << nb_bits) - 1u;
+        for (int d = lane; d < ND; d += 32) wc[warp][d] = 0;
+        __syncwarp();
+        for (int x = w0 + lane; x < w1; x += 32) smem_inc(&wc[warp][(key[ps == 0 ? x : (int)cur[x]] >> shift) & dm]);
+        __syncthreads();
+        {   // first free place per (digit, warp): thread t owns digit t
+            const int t = threadIdx.x;
+            int v = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) v += wc[w][t];
+            const int incl = warp_incl_scan(v);
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int run = incl - v;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) run += (w < warp) ? s_wsum[w] : 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const int c = wc[w][t];
+                wc[w][t] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        for (int base = w0; base < w1; base += 32) {
+            const bool act = base + lane < w1;
+            const int idx = act ? (ps == 0 ? base + lane : (int)cur[base + lane]) : 0;
+            const uint32_t d = act ? ((key[idx] >> shift) & dm) : 0u;
+            const uint32_t peers = digit_peers_bits(d, act, nb_bits);
+            if (act) nxt[wc[warp][d] + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)idx;
+            __syncwarp();
+            if (act && lane == (__ffs(peers) - 1)) wc[warp][d] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        uint16_t* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    for (int x = threadIdx.x; x < m; x += 256) {
+        const int o = P ? (int)cur[x] : x;
+        const uint32_t k = key[o];
+        const uint32_t prev = x > 0 ? key[P ? (int)cur[x - 1] : x - 1] : 0xFFFFFFFFu;
+        const int32_t agent = __ldcg(&src[lo + o].y);
+        const int32_t st = key_hi | (int32_t)k;
+        const int q = lo + x;
+        emit(q, st, agent);
+        if (prev != k) {  // first of its state: one 8-byte store of the bounds (on a 100M-state table every such store is a DRAM access)
+            int e = x + 1;
+            while (e < m && key[P ? (int)cur[e] : e] == k) ++e;
+            seg[st] = make_uint2((uint32_t)q, (uint32_t)(lo + e));
+        }
+    }
+    __syncthreads();
+}
+
+// ---- the buckets of this block: sort by the low bits, then positions, segment bounds and fresh writer records.
+//   * the low bits are ONE digit and the block has at most three buckets (the usual case on a table of <= 2^20 states): a
+//     team of two warps per bucket, all buckets of the grid in flight at once (flow_team_staged);
+//   * everything else -- more low bits (larger tables), buckets that herding made too large for a team, small grids -- is
+//     done bucket by bucket by the whole block in shared memory (flow_block_staged), and what does not even fit there by
+//     counting passes through global memory (flow_local_pass).
 constexpr int kWarpBucketMax = 3072;
 template <int WARPS>
 __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char* arena, int arena_bytes, const int* s_base, int* s_wsum,
@@ -388,63 +440,50 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
     const int L = X.local_passes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x, nb = gridDim.x;
-    // at most three buckets per block (the usual grid): a TEAM of two warps (2|3, 4|5, 6|7; warps 0 and 1 stay out -- warp
-    // 0 runs several times slower here) owns one and a third of the arena (two sets of counters + staging area)
-    const bool slots = (kRadix - 1) / nb < 3;
+    const bool teams = (kRadix - 1) / nb < 3 && L == 1 && !(X.flags & 1);
     const int slot_bytes = (arena_bytes / 3) & ~15;
-    const int team = slots ? (warp >= 2 ? (warp - 2) >> 1 : -1) : 0, tw = slots ? (warp & 1) : 0;
-    int* cnt = slots ? reinterpret_cast<int*>(arena + (size_t)(team >= 0 ? team : 0) * slot_bytes) : whist[warp];
-    const int stage_cap = min(((slot_bytes - 2 * (int)sizeof(int) * kRadix - 16) / 8) & ~7, 65535);
-    int* s_tot = cnt + 2 * kRadix;  // [2] (+ 2 words of padding)
-    uint32_t* sagent = reinterpret_cast<uint32_t*>(s_tot + 4);
-    uint16_t* sdigit = reinterpret_cast<uint16_t*>(sagent + stage_cap);
-    uint16_t* order = sdigit + stage_cap;
-    bool big = false;
-    for (int j = slots ? (team >= 0 ? team : WARPS * kRadix) : warp; j * nb + b < kRadix; j += WARPS) {
-        const int d = j * nb + b;
-        const int lo = s_base[d], hi = s_base[d + 1];
-        if (hi <= lo) continue;
-        if (hi - lo > kWarpBucketMax) { big = true; continue; }
-        if (L == 1 && slots && hi - lo <= stage_cap && !(X.flags & 1)) {  // (the same answer in both warps of the team)
-            flow_team_staged(tw, 1 + team, cnt, s_tot, sagent, sdigit, order, X.kv[1], X.kv[0], lo, hi, X.msd_shift,
-                             (int32_t)((uint32_t)d << X.msd_shift), X);
-            continue;
-        }
-        if (slots && tw) continue;  // everything else: one warp per bucket
-        int src = L & 1;
-        for (int ps = 0; ps < L; ++ps) {
-            const int shift = ps * kRadixBits;
-            flow_warp_pass(cnt, X.kv[src], X.kv[src ^ 1], lo, hi, shift, min(kRadixBits, X.msd_shift - shift), ps == L - 1, L == 1,
-                           (int32_t)((uint32_t)d << X.msd_shift), X);
-            src ^= 1;
-        }
-        const int2* fin = X.kv[0];
-        if (L == 0) {  // the bucket is one state, already in place
-            if (lane == 0) X.seg[d] = make_uint2((uint32_t)lo, (uint32_t)hi);
-            for (int q = lo + lane; q < hi; q += 32) {
-                const int2 e = __ldcg(fin + q);
-                X.pos[e.y] = q;
-                X.rec[q] = (uint64_t)(uint32_t)e.y;
-            }
-        } else if (L > 1) {  // bounds from the neighbours in the finished order
-            for (int q = lo + lane; q < hi; q += 32) {
-                const int32_t k = __ldcg(&fin[q].x);
-                const int32_t prev = q > lo ? __ldcg(&fin[q - 1].x) : -1, next = q + 1 < hi ? __ldcg(&fin[q + 1].x) : -1;
-                if (prev != k) X.seg[k].x = (uint32_t)q;
-                if (next != k) X.seg[k].y = (uint32_t)(q + 1);
-            }
+    const int stage_cap = min(min(((slot_bytes - 2 * (int)sizeof(int) * kRadix - 16) / 8) & ~7, 65535), kWarpBucketMax);
+    bool rest = !teams;
+    if (teams) {  // teams 2|3, 4|5, 6|7 (warps 0 and 1 stay out -- warp 0 runs several times slower here)
+        const int team = warp >= 2 ? (warp - 2) >> 1 : -1, tw = warp & 1;
+        int* cnt = reinterpret_cast<int*>(arena + (size_t)(team >= 0 ? team : 0) * slot_bytes);
+        int* s_tot = cnt + 2 * kRadix;  // [2] (+ 2 words of padding)
+        uint32_t* sagent = reinterpret_cast<uint32_t*>(s_tot + 4);
+        uint16_t* sdigit = reinterpret_cast<uint16_t*>(sagent + stage_cap);
+        uint16_t* order = sdigit + stage_cap;
+        const int d = team * nb + b;
+        if (team >= 0 && d < kRadix) {
+            const int lo = s_base[d], hi = s_base[d + 1];
+            if (hi - lo > stage_cap) rest = true;
+            else if (hi > lo)
+                flow_team_staged(tw, 1 + team, cnt, s_tot, sagent, sdigit, order, X.kv[1], X.kv[0], lo, hi, X.msd_shift,
+                                 (int32_t)((uint32_t)d << X.msd_shift), X);
         }
     }
-    if (!__syncthreads_or(big)) return;
-    if (threadIdx.x == 0) atomicAdd(X.ctr + 10, 1u);  // blocks with a large bucket
+    if (!__syncthreads_or(rest)) return;
+    const int block_cap = min(flow_block_cap(arena_bytes), 65535);
+    auto emit = [&](int q, int32_t st, int32_t agent) {
+        X.kv[0][q] = make_int2(st, agent);
+        X.pos[agent] = q;
+        X.rec[q] = (uint64_t)(uint32_t)agent;
+    };
     for (int d = b; d < kRadix; d += nb) {
         const int lo = s_base[d], hi = s_base[d + 1];
-        if (hi - lo <= kWarpBucketMax) continue;  // (uniform)
-        int src = L & 1;
+        if (hi <= lo || (teams && hi - lo <= stage_cap)) continue;  // (uniform; the teams have done theirs)
+        const int32_t key_hi = (int32_t)((uint32_t)d << X.msd_shift);
+        if (hi - lo <= block_cap) {  // the scatter left the bucket in kv[1] (kv[0] when there are no low bits: nothing moves then)
+            flow_block_staged<WARPS>(arena, arena_bytes, s_wsum, X.kv[L ? 1 : 0], lo, hi, X.msd_shift, key_hi, X.seg, emit);
+            continue;
+        }
+        int src = L ? 1 : 0;
         for (int ps = 0; ps < L; ++ps) {
             const int shift = ps * kRadixBits;
             flow_local_pass<WARPS>(whist, s_wsum, X.kv[src], X.kv[src ^ 1], lo, hi, shift, min(kRadixBits, X.msd_shift - shift));
             src ^= 1;
+        }
+        if (src != 0) {  // (an even number of passes ends in kv[1])
+            for (int q = lo + threadIdx.x; q < hi; q += blockDim.x) X.kv[0][q] = __ldcg(X.kv[1] + q);
+            __syncthreads();
         }
         const int2* fin = X.kv[0];
         for (int q = lo + threadIdx.x; q < hi; q += blockDim.x) {
@@ -522,7 +561,7 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
             grid.sync();
             flow_scan<WARPS>(X);
             grid.sync();
-            flow_scatter<WARPS>(s_whist, s_base, s_wsum, F.st_a, n, X.kv[X.local_passes & 1], X);
+            flow_scatter<WARPS>(s_whist, s_base, s_wsum, F.st_a, n, X.kv[X.local_passes ? 1 : 0], X);
             grid.sync();
             flow_buckets<WARPS>(s_whist, s_arena, (int)(flow_smem_bytes(LPR) - sizeof(int) * (kRadix + 8)), s_base, s_wsum, X);
             grid.sync();
@@ -942,7 +981,7 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
 
         // ---------------- the next step's order: stable scatter into the buckets, then every bucket inside one block
         if (tid == 0) { X.ctr[0] = 0u; X.ctr[1] = 0u; X.ctr[2] = 0u; }  // (idle since the last barrier; next used after two more)
-        flow_scatter<WARPS>(s_whist, s_base, s_wsum, nxt, n, X.kv[X.local_passes & 1], X);
+        flow_scatter<WARPS>(s_whist, s_base, s_wsum, nxt, n, X.kv[X.local_passes ? 1 : 0], X);
         grid.sync();
         if (clk && k < 10) F.phase_ns[32 + k] = global_ns();
         flow_buckets<WARPS>(s_whist, s_arena, (int)(flow_smem_bytes(LPR) - sizeof(int) * (kRadix + 8)), s_base, s_wsum, X);

@@ -29,7 +29,7 @@ static int sfail(int code, const char* fmt, ...) {
 struct qe_shard {
     int rank = 0, world = 0, device = 0, sms = 0;
     int64_t S = 0, rows = 0;
-    int A = 0, ld = 0, lpr = 0, passes = 0;
+    int A = 0, ld = 0, lpr = 0, passes = 0, msd_shift = 0;
     int n_total = 0, n_home = 0, nh = 0;
     float gamma = 0.0f;
     uint32_t env_seed = 0;
@@ -168,6 +168,7 @@ int qe_shard_create(int64_t num_states, int32_t num_actions, float discount_fact
     int bits = 1;
     while (bits < 31 && (1ll << bits) < s->rows) ++bits;
     s->passes = (bits + kRadixBits - 1) / kRadixBits;
+    s->msd_shift = bits > kRadixBits ? bits - kRadixBits : 0;
     cudaDeviceProp prop;
     SCK(cudaGetDeviceProperties(&prop, device));
     s->sms = prop.multiProcessorCount;
@@ -317,7 +318,7 @@ int qe_shard_steps(qe_shard_t* const* ranks, int32_t nlocal, int32_t steps, cons
     if (bpr < 1) return sfail(QE_ERR_CUDA, "not enough resident blocks for %d ranks", nlocal);
     ShardArgs H{};
     H.G = G; H.first_rank = s0->rank; H.nlocal = nlocal; H.blocks_per_rank = bpr; H.multi_device = nlocal == 1 && G > 1;
-    H.A = s0->A; H.ld = s0->ld; H.passes = s0->passes;
+    H.A = s0->A; H.ld = s0->ld; H.passes = s0->passes; H.msd_shift = s0->msd_shift;
     H.n_total = s0->n_total; H.n_home = s0->n_home; H.S = s0->S; H.rows = s0->rows;
     H.steps = steps; H.eps_thresh = s0->d_thresh; H.lr = s0->d_lr;
     H.stream_seed = stream_seed; H.t0 = s0->t; H.env_stream_seed = env_stream_seed; H.env_t0 = s0->t; H.env_seed = s0->env_seed;

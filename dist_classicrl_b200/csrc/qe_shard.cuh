@@ -22,7 +22,7 @@
 // Hash MDP only (the environment of config 4); results are identical to the single-GPU engine and to the reference's
 // sequential loop in global agent order.
 #pragma once
-#include "qe_pipe.cuh"
+#include "qe_flow.cuh"
 
 namespace qe {
 
@@ -56,7 +56,7 @@ struct ShardLocal {          // private to a rank
 };
 struct ShardArgs {
     int G, first_rank, nlocal, blocks_per_rank, multi_device;
-    int A, ld, passes;
+    int A, ld, passes, msd_shift;  // msd_shift: bucket of a state inside its shard = state >> msd_shift (< kRadix)
     int n_total, n_home;     // agents, agents per rank (ceil)
     int64_t S, rows;         // states, states per shard (ceil)
     int steps;
@@ -138,15 +138,19 @@ __device__ __forceinline__ void shard_xsync(cg::grid_group& grid, const ShardArg
     }
 }
 
-// The owner's local stable radix sort of its inbox (pipe_sort of qe_pipe.cuh with pairs as input, blocks counted inside
-// the rank's group of CTAs, and every agent's final position stored into its HOME rank's slab).
+// The owner's local stable sort of its inbox, MSD first (the bucket sort of qe_flow.cuh with pairs as input, blocks
+// counted inside the rank's group of CTAs): ONE pass over the grid partitions the pairs by the top (up to) 10 bits of the
+// state -- per-warp digit counts, column scan over the group's blocks, stable scatter --, then every bucket is sorted by
+// its low bits by one CTA in shared memory (flow_block_staged), which also writes the segment bounds and stores every
+// agent's position into its HOME rank's slab.  (Round 2's first version ran one such grid-wide pass per 10 bits: three
+// passes of ~40 us fixed cost each on the 100M-state table, whatever the number of keys.)  The finished order is in kv[0].
 template <int WARPS>
-__device__ __forceinline__ int shard_sort(cg::grid_group& grid, int (*whist)[kRadix], int* s_base, int* s_wsum, int n, int old_n,
-                                          const ShardArgs& H, const ShardLocal& L, int me, int b, int nb) {
+__device__ __forceinline__ void shard_sort(cg::grid_group& grid, int (*whist)[kRadix], unsigned char* arena, int arena_bytes, int* s_base, int* s_wsum,
+                                           int n, int old_n, const ShardArgs& H, const ShardLocal& L, int me, int b, int nb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ShardPeer& own = H.peer[me];
-    if (old_n > 0) {  // reset the bounds of the previous order (still in kv[passes & 1])
-        const int2* old = L.kv[H.passes & 1];
+    if (old_n > 0) {  // reset the bounds of the previous order (still in kv[0])
+        const int2* old = L.kv[0];
         for (int q = b * blockDim.x + threadIdx.x; q < old_n; q += nb * blockDim.x) {
             const int32_t kq = __ldcg(&old[q].x);
             if (q == 0 || __ldcg(&old[q - 1].x) != kq) own.seg[kq] = make_uint2(0u, 0u);
@@ -155,113 +159,138 @@ __device__ __forceinline__ int shard_sort(cg::grid_group& grid, int (*whist)[kRa
     const int chunk = ((n + nb - 1) / nb + 31) & ~31;
     const int part = ((chunk / 32 + WARPS - 1) / WARPS) * 32;
     const int lo = min(b * chunk + warp * part, n), hi = min(min(b * chunk + (warp + 1) * part, (b + 1) * chunk), n);
-    int src = 0;
-    for (int ps = 0; ps < H.passes; ++ps) {
-        const bool last = ps == H.passes - 1;
-        const int shift = ps * kRadixBits;
-        const int2* in = ps == 0 ? own.inbox : L.kv[src];
-        int2* out = L.kv[src ^ 1];
-        auto load_pair = [&](int x) {
-            int2 e = make_int2(0, 0);
-            if (x < hi) e = __ldcg(in + x);
-            return e;
-        };
-        for (int d = lane; d < kRadix; d += 32) whist[warp][d] = 0;
-        __syncwarp();
-        for (int base = lo; base < hi; base += 256) {
-            int2 e[8];
+    const int shift = H.msd_shift;
+    const int2* in = own.inbox;
+    int2* out = L.kv[shift ? 1 : 0];
+    auto load_pair = [&](int x) {
+        int2 e = make_int2(0, 0);
+        if (x < hi) e = __ldcg(in + x);
+        return e;
+    };
+    for (int d = lane; d < kRadix; d += 32) whist[warp][d] = 0;
+    __syncwarp();
+    for (int base = lo; base < hi; base += 256) {
+        int2 e[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) e[u] = load_pair(base + 32 * u + lane);
+        for (int u = 0; u < 8; ++u) e[u] = load_pair(base + 32 * u + lane);
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (base + 32 * u + lane < hi) atomicAdd(&whist[warp][((uint32_t)e[u].x >> shift) & (kRadix - 1)], 1);
-        }
-        __syncthreads();
-        for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
-            int t = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) t += whist[w][d];
-            L.ghist[(size_t)d * nb + b] = t;
-        }
-        grid.sync();
-        {
-            const int gw = b * WARPS + warp, nw = nb * WARPS;
-            const int per = (nb + 31) / 32;
-            for (int d = gw; d < kRadix; d += nw) {
-                int* row = L.ghist + (size_t)d * nb;
-                int v[kScanPerLane];
-                int sum = 0;
-#pragma unroll
-                for (int j = 0; j < kScanPerLane; ++j) {
-                    const int x = lane * per + j;
-                    v[j] = (j < per && x < nb) ? __ldcg(row + x) : 0;
-                }
-#pragma unroll
-                for (int j = 0; j < kScanPerLane; ++j) sum += v[j];
-                const int incl = warp_incl_scan(sum);
-                int run = incl - sum;
-#pragma unroll
-                for (int j = 0; j < kScanPerLane; ++j) {
-                    const int x = lane * per + j;
-                    if (j < per && x < nb) row[x] = run;
-                    run += v[j];
-                }
-                if (lane == 31) L.rowtot[d] = incl;
-            }
-        }
-        grid.sync();
-        {
-            const int4 v4 = __ldcg(reinterpret_cast<const int4*>(L.rowtot) + threadIdx.x);
-            const int v[4] = {v4.x, v4.y, v4.z, v4.w};
-            const int sum = v4.x + v4.y + v4.z + v4.w;
-            const int incl = warp_incl_scan(sum);
-            if (lane == 31) s_wsum[warp] = incl;
-            __syncthreads();
-            int before = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) before += (w < warp) ? s_wsum[w] : 0;
-            int run = before + incl - sum;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { s_base[threadIdx.x * 4 + j] = run; run += v[j]; }
-        }
-        __syncthreads();
-        for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
-            int run = s_base[d] + __ldcg(L.ghist + (size_t)d * nb + b);
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                const int c = whist[w][d];
-                whist[w][d] = run;
-                run += c;
-            }
-        }
-        __syncthreads();
-        for (int base = lo; base < hi; base += 256) {
-            int2 e[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) e[u] = load_pair(base + 32 * u + lane);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int x = base + 32 * u + lane;
-                const bool act = x < hi;
-                const uint32_t d = ((uint32_t)e[u].x >> shift) & (kRadix - 1);
-                const uint32_t peers = digit_peers(d, act);
-                if (act) {
-                    const int p = whist[warp][d] + __popc(peers & ((1u << lane) - 1u));
-                    out[p] = e[u];
-                    if (last) {  // the agent's home rank learns where its record goes
-                        const int hr = e[u].y / H.n_home;
-                        H.peer[hr].pos[e[u].y - hr * H.n_home] = p;
-                    }
-                }
-                __syncwarp();
-                if (act && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
-                __syncwarp();
-            }
-        }
-        grid.sync();
-        src ^= 1;
+        for (int u = 0; u < 8; ++u)
+            if (base + 32 * u + lane < hi) smem_inc(&whist[warp][((uint32_t)e[u].x >> shift) & (kRadix - 1)]);
     }
-    return src;
+    __syncthreads();
+    for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) t += whist[w][d];
+        L.ghist[(size_t)d * nb + b] = t;
+    }
+    grid.sync();
+    {
+        const int per = (nb + 31) / 32;
+        for (int d = b + warp * nb; d < kRadix; d += WARPS * nb) {  // (bucket d: warp d / nb of the group's block d % nb)
+            int* row = L.ghist + (size_t)d * nb;
+            int v[kScanPerLane];
+            int sum = 0;
+#pragma unroll
+            for (int j = 0; j < kScanPerLane; ++j) {
+                const int x = lane * per + j;
+                v[j] = (j < per && x < nb) ? __ldcg(row + x) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < kScanPerLane; ++j) sum += v[j];
+            const int incl = warp_incl_scan(sum);
+            int run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < kScanPerLane; ++j) {
+                const int x = lane * per + j;
+                if (j < per && x < nb) row[x] = run;
+                run += v[j];
+            }
+            if (lane == 31) L.rowtot[d] = incl;
+        }
+    }
+    grid.sync();
+    {
+        const int4 v4 = __ldcg(reinterpret_cast<const int4*>(L.rowtot) + threadIdx.x);
+        const int v[4] = {v4.x, v4.y, v4.z, v4.w};
+        const int sum = v4.x + v4.y + v4.z + v4.w;
+        const int incl = warp_incl_scan(sum);
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) before += (w < warp) ? s_wsum[w] : 0;
+        int run = before + incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s_base[threadIdx.x * 4 + j] = run; run += v[j]; }
+        if (threadIdx.x == 255) s_base[kRadix] = run;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
+        int run = s_base[d] + __ldcg(L.ghist + (size_t)d * nb + b);
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const int c = whist[w][d];
+            whist[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int base = lo; base < hi; base += 256) {
+        int2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] = load_pair(base + 32 * u + lane);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int x = base + 32 * u + lane;
+            if (base + 32 * u >= hi) break;  // (uniform)
+            const bool act = x < hi;
+            const uint32_t d = ((uint32_t)e[u].x >> shift) & (kRadix - 1);
+            const uint32_t peers = digit_peers(d, act);
+            if (act) out[whist[warp][d] + __popc(peers & ((1u << lane) - 1u))] = e[u];
+            __syncwarp();
+            if (act && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
+            __syncwarp();
+        }
+    }
+    grid.sync();
+    // ---- the buckets of this block, one after the other
+    auto emit = [&](int q, int32_t st, int32_t agent) {
+        L.kv[0][q] = make_int2(st, agent);
+        const int hr = agent / H.n_home;  // the agent's home rank learns where its record goes
+        H.peer[hr].pos[agent - hr * H.n_home] = q;
+    };
+    const int block_cap = min(flow_block_cap(arena_bytes), 65535);
+    const int Lp = (shift + kRadixBits - 1) / kRadixBits;
+    for (int d = b; d < kRadix; d += nb) {
+        const int blo = s_base[d], bhi = s_base[d + 1];
+        if (bhi <= blo) continue;  // (uniform)
+        const int32_t key_hi = (int32_t)((uint32_t)d << shift);
+        if (bhi - blo <= block_cap) {
+            flow_block_staged<WARPS>(arena, arena_bytes, s_wsum, L.kv[shift ? 1 : 0], blo, bhi, shift, key_hi, own.seg, emit);
+            continue;
+        }
+        int src = Lp ? 1 : 0;  // (too large for shared memory: counting passes through global memory)
+        for (int ps = 0; ps < Lp; ++ps) {
+            const int sh = ps * kRadixBits;
+            flow_local_pass<WARPS>(whist, s_wsum, L.kv[src], L.kv[src ^ 1], blo, bhi, sh, min(kRadixBits, shift - sh));
+            src ^= 1;
+        }
+        if (src != 0) {
+            for (int q = blo + threadIdx.x; q < bhi; q += blockDim.x) L.kv[0][q] = __ldcg(L.kv[1] + q);
+            __syncthreads();
+        }
+        const int2* fin = L.kv[0];
+        for (int q = blo + threadIdx.x; q < bhi; q += blockDim.x) {
+            const int2 e = __ldcg(fin + q);
+            const int32_t prev = q > blo ? __ldcg(&fin[q - 1].x) : -1, next = q + 1 < bhi ? __ldcg(&fin[q + 1].x) : -1;
+            const int hr = e.y / H.n_home;
+            H.peer[hr].pos[e.y - hr * H.n_home] = q;
+            if (prev != e.x) own.seg[e.x].x = (uint32_t)q;
+            if (next != e.x) own.seg[e.x].y = (uint32_t)(q + 1);
+        }
+        __syncthreads();
+    }
 }
 template <int WARPS>
 __device__ __forceinline__ void shard_bounds(const int2* sorted, int n, uint2* seg, int b, int nb) {
@@ -294,7 +323,11 @@ __device__ __forceinline__ void shard_bounds(const int2* sorted, int n, uint2* s
     }
 }
 
-__host__ __device__ constexpr size_t shard_smem_bytes(int lpr) { return pipe_smem_bytes(lpr); }
+// dynamic shared memory: the phase layouts of the pipelined form, and room for the bucket sorts (counters + 8 bytes per key
+// of a bucket of ~5600 keys: one rank alone on the 100M-state table has 4096 per bucket) with the bucket starts behind it
+__host__ __device__ constexpr size_t shard_smem_bytes(int lpr) {
+    return pipe_smem_bytes(lpr) > (size_t)57344 ? pipe_smem_bytes(lpr) : (size_t)57344;
+}
 
 template <int LPR>
 __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
@@ -307,7 +340,8 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
     __shared__ unsigned int s_off[kMaxRanks];  // where this rank's pairs start in every owner's inbox
     extern __shared__ __align__(16) float s_mem[];
     int (*s_whist)[kRadix] = reinterpret_cast<int (*)[kRadix]>(s_mem);
-    int* s_base = reinterpret_cast<int*>(s_mem) + WARPS * kRadix;
+    constexpr int kArenaBytes = (int)(shard_smem_bytes(LPR) - sizeof(int) * (kRadix + 8));
+    int* s_base = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_mem) + kArenaBytes);  // [kRadix + 1] bucket starts of the local sort
     float* s_row = s_mem;
     uint32_t* s_touch = reinterpret_cast<uint32_t*>(s_mem) + 8 * LPR * 256;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -450,8 +484,7 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
     // S4 + S5: the owner's local sort, positions to the home ranks, segment bounds
     auto local_sort = [&]() {
         n_in = n_next;
-        const int src = shard_sort<WARPS>(grid, s_whist, s_base, s_wsum, n_in, old_n, H, L, me, b, nb);
-        shard_bounds<WARPS>(L.kv[src], n_in, own.seg, b, nb);
+        shard_sort<WARPS>(grid, s_whist, reinterpret_cast<unsigned char*>(s_mem), kArenaBytes, s_base, s_wsum, n_in, old_n, H, L, me, b, nb);
         old_n = n_in;
         if (rtid == 0) L.ctr[1] = (unsigned int)n_in;
     };
@@ -480,7 +513,7 @@ __global__ void __launch_bounds__(256, 3) shard_kernel(ShardArgs H) {
         const uint32_t t_sel = H.t0 + (uint32_t)k, t_env = H.env_t0 + (uint32_t)k;
         const uint64_t thresh = H.eps_thresh[k];
         const float lr = H.lr[k];
-        const int2* sorted = L.kv[H.passes & 1];
+        const int2* sorted = L.kv[0];
         double loc_sum = 0.0;
         unsigned int loc_cnt = 0;
 

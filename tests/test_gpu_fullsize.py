@@ -154,7 +154,7 @@ def test_config3_chunking_and_determinism(capi):
 
 
 @pytest.mark.parametrize("form", ["0", "1", "3", "5"])
-@pytest.mark.parametrize("S,A,N,steps", [(2000, 16, 50_000, 24), (97, 5, 4096, 16), (300_000, 8, 200_000, 10), (3, 20, 1000, 6), (70_000, 32, 33, 40)])
+@pytest.mark.parametrize("S,A,N,steps", [(2000, 16, 50_000, 24), (97, 5, 4096, 16), (300_000, 8, 200_000, 10), (3, 20, 1000, 6), (70_000, 32, 33, 40), (3_000_000, 4, 150_000, 8)])
 def test_all_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form, S, A, N, steps):
     """QE_FORM pins the form of the TD update (0 = writer lists, 1 = per-step sort, 3 = target pipeline, 5 = one-pass form); all must
     reproduce the oracle bit for bit, also when hundreds of agents herd on one row (or all of them on three rows)."""
