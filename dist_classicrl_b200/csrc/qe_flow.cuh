@@ -745,33 +745,38 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
                     bool go = p < pe, fin = !go;  // nobody (left) on s': the row is as the replay has it
                     const uint32_t pa = p & ~3u;
                     FLOW_STAT(const uint32_t p0 = p;)
-                    U8 e4;
+                    U8 e4, e5;  // (a long prefix -- a herded row -- is read two groups per pass: both loads travel together)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) e4.w[j] = 0u;
+                    for (int j = 0; j < 8; ++j) e4.w[j] = e5.w[j] = 0u;
                     if (go) e4 = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa));
+                    if (go && pa + 4u < pe) e5 = ld_relaxed_v8(reinterpret_cast<const uint2*>(rec + pa + 4));
                     if (fresh) {
                         cp_async_wait_all();
                         fresh = false;
                         FLOW_STAT(++st_fresh;)
                     }
+                    auto replay4 = [&](const U8& g, const uint32_t base) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t ex = e4.w[2 * j], ey = e4.w[2 * j + 1];
-                        if (go && pa + j >= p) {
-                            if (pa + j >= pe || (int)(ex & kRecAgent) >= i) {
-                                fin = true;  // the segment ends here, or the writers from here on come after i
-                                go = false;
-                            } else if (ex & (kRecFinal | kRecSelf)) {
-                                const float tg = (ex & kRecFinal) ? __uint_as_float(ey) : td_target_s(__uint_as_float(ey), row_max(), F.gamma);
-                                const uint32_t a2 = (ex >> 24) & 31u;
-                                float* cell = myrow + a2;
-                                *cell = td_from_target_s(*cell, tg, lr);
-                                ++p;
-                            } else {
-                                go = false;  // an earlier writer that has not published yet
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t ex = g.w[2 * j], ey = g.w[2 * j + 1];
+                            if (go && base + j >= p) {
+                                if (base + j >= pe || (int)(ex & kRecAgent) >= i) {
+                                    fin = true;  // the segment ends here, or the writers from here on come after i
+                                    go = false;
+                                } else if (ex & (kRecFinal | kRecSelf)) {
+                                    const float tg = (ex & kRecFinal) ? __uint_as_float(ey) : td_target_s(__uint_as_float(ey), row_max(), F.gamma);
+                                    const uint32_t a2 = (ex >> 24) & 31u;
+                                    float* cell = myrow + a2;
+                                    *cell = td_from_target_s(*cell, tg, lr);
+                                    ++p;
+                                } else {
+                                    go = false;  // an earlier writer that has not published yet
+                                }
                             }
                         }
-                    }
+                    };
+                    replay4(e4, pa);
+                    if (go && p == pa + 4u && p < pe) replay4(e5, pa + 4u);  // (no vote here: this code runs under `if (busy)`, not all lanes are present)
                     if (go && p >= pe) fin = true;
                     FLOW_STAT(st_prog += (fin || p != p0) ? 1u : 0u; st_block += (!fin && p == p0) ? 1u : 0u;)
                     if (fin) {

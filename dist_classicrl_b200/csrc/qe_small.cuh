@@ -181,7 +181,11 @@ __global__ void __launch_bounds__(kSmallMaxAgents) fused_small_kernel(Table T, F
 #pragma unroll
             for (int w = 0; w < WORDS; ++w) dm[w] = 0u;
         }
-        for (int round = 0; round <= n; ++round) {
+        // Rounds are per WARP (a round ends at a vote of the warp, not at a block barrier): a warp re-reads the flags of the
+        // agents it waits for -- volatile shared memory, written target first, flag second -- until none of its lanes is
+        // pending.  Dependencies point to smaller agent indices, so the warp that holds the smallest pending agent never
+        // waits for anybody who waits: no deadlock; the bound only catches a broken invariant.
+        for (int round = 0; round < (1 << 22); ++round) {
             bool now = false;
             if (pending) {
                 // ready when every earlier writer of s' has its target, or is a self loop on s' (derived in line below)
@@ -212,9 +216,10 @@ __global__ void __launch_bounds__(kSmallMaxAgents) fused_small_kernel(Table T, F
                 s_ok[i] = 1;
                 pending = false;
             }
-            if (__syncthreads_count(pending) == 0) break;
+            if (!__any_sync(kFull, pending)) break;
         }
         if (pending) atomicOr(T.err, kErrTimeout);
+        __syncthreads();  // every target is out before the commit reads them
 
         // ---------------- phase 3: commit, the first writer of every cell replays all of its writers in agent order
         if (act) {
