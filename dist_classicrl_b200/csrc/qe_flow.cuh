@@ -427,6 +427,32 @@ __device__ __forceinline__ void flow_block_staged(unsigned char* arena, int aren
     __syncthreads();
 }
 
+// ---- one warp, one bucket of at most 32 keys (small batches: most buckets of a grid of a few blocks): every lane ranks its
+// key against the other lanes' (stable: equal keys keep their order), no shared memory, no barrier.
+template <class Emit>
+__device__ __forceinline__ void flow_warp_tiny(const int2* src, int lo, int hi, int bits, int32_t key_hi, uint2* seg, Emit emit) {
+    const int lane = threadIdx.x & 31;
+    const int m = hi - lo;
+    const uint32_t mask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+    int2 e = make_int2(0, 0);
+    if (lane < m) e = __ldcg(src + lo + lane);
+    const uint32_t k = lane < m ? ((uint32_t)e.x & mask) : 0xFFFFFFFFu;
+    int rank = 0, before = 0, equal = 0;
+    for (int j = 0; j < m; ++j) {
+        const uint32_t kj = __shfl_sync(kFull, k, j);
+        rank += (kj < k) ? 1 : 0;
+        before += (kj == k && j < lane) ? 1 : 0;
+        equal += (kj == k) ? 1 : 0;
+    }
+    __syncwarp();  // (src may be the buffer the order is written to: every lane has its element by now)
+    if (lane < m) {
+        const int32_t st = key_hi | (int32_t)k;
+        const int q = lo + rank + before;
+        emit(q, st, e.y);
+        if (before == 0) seg[st] = make_uint2((uint32_t)q, (uint32_t)(q + equal));
+    }
+}
+
 // ---- the buckets of this block: sort by the low bits, then positions, segment bounds and fresh writer records.
 //   * the low bits are ONE digit and the block has at most three buckets (the usual case on a table of <= 2^20 states): a
 //     team of two warps per bucket, all buckets of the grid in flight at once (flow_team_staged);
@@ -460,16 +486,25 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
                                  (int32_t)((uint32_t)d << X.msd_shift), X);
         }
     }
-    if (!__syncthreads_or(rest)) return;
-    const int block_cap = min(flow_block_cap(arena_bytes), 65535);
     auto emit = [&](int q, int32_t st, int32_t agent) {
         X.kv[0][q] = make_int2(st, agent);
         X.pos[agent] = q;
         X.rec[q] = (uint64_t)(uint32_t)agent;
     };
+    if (!teams) {  // buckets of at most 32 keys: one warp each (a grid of a few blocks has hundreds of them per block)
+        rest = false;
+        for (int j = warp; j * nb + b < kRadix; j += WARPS) {
+            const int d = j * nb + b;
+            const int lo = s_base[d], hi = s_base[d + 1];
+            if (hi - lo > 32) rest = true;
+            else if (hi > lo) flow_warp_tiny(X.kv[L ? 1 : 0], lo, hi, X.msd_shift, (int32_t)((uint32_t)d << X.msd_shift), X.seg, emit);
+        }
+    }
+    if (!__syncthreads_or(rest)) return;
+    const int block_cap = min(flow_block_cap(arena_bytes), 65535);
     for (int d = b; d < kRadix; d += nb) {
         const int lo = s_base[d], hi = s_base[d + 1];
-        if (hi <= lo || (teams && hi - lo <= stage_cap)) continue;  // (uniform; the teams have done theirs)
+        if (hi <= lo || (teams ? hi - lo <= stage_cap : hi - lo <= 32)) continue;  // (uniform; the teams / single warps have done theirs)
         const int32_t key_hi = (int32_t)((uint32_t)d << X.msd_shift);
         if (hi - lo <= block_cap) {  // the scatter left the bucket in kv[1] (kv[0] when there are no low bits: nothing moves then)
             flow_block_staged<WARPS>(arena, arena_bytes, s_wsum, X.kv[L ? 1 : 0], lo, hi, X.msd_shift, key_hi, X.seg, emit);
