@@ -1037,6 +1037,16 @@ static __global__ void serve_bootstrap_kernel(Table T, const int32_t* __restrict
 // replicated table: delta[s][a] = Q[s][a] - base[s][a]   (dense [S][A] buffers)
 static __global__ void table_delta_kernel(Table T, int64_t S, const float* __restrict__ base, float* __restrict__ delta) {
     const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
+    if (T.ld == T.A) {  // rows without padding (A = 8, 16, 32): the table IS the dense array, 16 bytes per lane and access
+        const float4* q4 = reinterpret_cast<const float4*>(T.q);
+        const float4* b4 = reinterpret_cast<const float4*>(base);
+        float4* d4 = reinterpret_cast<float4*>(delta);
+        for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total / 4; x += stride) {
+            const float4 a = q4[x], b = b4[x];
+            d4[x] = make_float4(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w));
+        }
+        return;
+    }
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
         const size_t s = x / T.A;
         delta[x] = __fsub_rn(T.q[s * T.ld + (x - s * T.A)], base[x]);
@@ -1045,6 +1055,18 @@ static __global__ void table_delta_kernel(Table T, int64_t S, const float* __res
 // ... and Q = base = base + sum of the ranks' deltas
 static __global__ void table_merge_kernel(Table T, int64_t S, float* __restrict__ base, const float* __restrict__ delta_sum) {
     const size_t total = (size_t)S * T.A, stride = (size_t)gridDim.x * blockDim.x;
+    if (T.ld == T.A) {
+        float4* q4 = reinterpret_cast<float4*>(T.q);
+        float4* b4 = reinterpret_cast<float4*>(base);
+        const float4* d4 = reinterpret_cast<const float4*>(delta_sum);
+        for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total / 4; x += stride) {
+            const float4 b = b4[x], d = d4[x];
+            const float4 v = make_float4(__fadd_rn(b.x, d.x), __fadd_rn(b.y, d.y), __fadd_rn(b.z, d.z), __fadd_rn(b.w, d.w));
+            b4[x] = v;
+            q4[x] = v;
+        }
+        return;
+    }
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
         const size_t s = x / T.A;
         const float v = __fadd_rn(base[x], delta_sum[x]);

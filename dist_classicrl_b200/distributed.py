@@ -535,7 +535,7 @@ class ReplicatedQLearning:
         # still merges every sync_every steps) instead of merging at the end of every call
         self.carry_over, self._since_sync = bool(carry_over), 0
         # (Round 1 pinned the per-step-sort form here so that ranks probing different forms would not wait for each other
-        # at the all-reduce; the engine's default form, the target pipeline, is one form on every rank.)
+        # at the all-reduce; the engine's default form, the one-pass pipeline, is one form on every rank.)
         self.rebase()
 
     def _stream(self):
