@@ -11,8 +11,9 @@
 //     written by the commit, so "select" of agent i may run while the targets of agents j < i are still being resolved:
 //     the row gathers of select (throughput) and the publish -> poll hops of the targets (latency) overlap, the
 //     per-agent hand-over array between the phases (16 B per agent each way) and one grid barrier are gone.  A warp
-//     claims a chunk, selects and steps its 32 agents, fetches their bootstrap rows into shared memory and polls the
-//     writer records of s'_i until every lane has published its target; then it claims the next chunk.
+//     claims a chunk, selects and steps its 32 agents and leaves them in a queue in shared memory; a free lane takes the
+//     next queue entry, fetches its bootstrap row into shared memory (cp.async) beside the first poll of the writer
+//     records of s'_i, and keeps polling until it has published its target -- a waiting agent holds up a lane, not a chunk.
 //   * a writer record is one 64-bit word {agent | action << 24 | flags, value}: the sort of the previous step leaves
 //     {agent, 0} at every position, the agent's warp overwrites it once with FINAL (value = target; terminated agents
 //     at once, QLO:760-766) and before that, for a self loop (s' = s), with SELF (value = reward: the reader derives
@@ -20,8 +21,10 @@
 //     256-bit load per four records: no separate "pending" pass, no barrier between filing and reading.
 //   * the order of the next states is an MSD bucket sort instead of LSD passes over the grid: the top (up to) 10 bits
 //     are a stable partition over all CTAs (digit counts per CTA taken in the tail of the in-order pass, column scan
-//     beside the commit, scatter), the remaining bits are sorted bucket by bucket inside one CTA with block barriers
-//     only; the same CTA then writes position, segment bounds and the initial writer records of its bucket.
+//     beside the commit, scatter), the remaining bits are sorted bucket by bucket inside one CTA -- by a team of two
+//     warps (one digit of low bits), by the whole CTA in shared memory (more bits, herded buckets) or by one warp in
+//     registers (tiny buckets of small batches) -- which also writes position, segment bounds and the initial writer
+//     records of its bucket.
 //
 // Per vector step:   [ select + step + targets | digit counts ]  B  [ column scan, commit ]  B  [ scatter ]  B
 //                    [ bucket sorts, positions, bounds, records ]  B
@@ -40,7 +43,7 @@ struct FlowScratch {
     uint64_t* rec;        // [cap + 8] writer records by sorted position (see above)
     uint2* seg;           // [S] per state {segment start, segment end} ({0, 0}: nobody stands on the state)
     int32_t* pos;         // [cap] agent -> sorted position
-    int2* kv[2];          // [cap] {state, agent} by position; the finished order is always in kv[0]
+    int2* kv[2];          // [cap] {state, agent} by position; the finished order is always in kv[0] (the scatter leaves the buckets in kv[1])
     int* ghist;           // [kRadix][blocks] bucket counts per block, scanned in place
     int* rowtot;          // [kRadix] bucket totals
     unsigned int* ctr;    // [64] 0: chunk claims; 1: chunks selected + stepped; 2: commit tile claims; 4: abort; 6: order invalid
@@ -48,7 +51,7 @@ struct FlowScratch {
     int local_passes;     // LSD passes (kRadixBits each) over the low msd_shift bits inside a bucket
     int sorted_valid;     // pos / seg / kv[0] / rec describe the states this launch starts from (to be checked)
     int old_n;            // agents of the order kv[0] and seg[] still describe (0: none, seg[] is all-empty)
-    int flags;            // development switches (QE_FLOW_FLAGS): 1 = no shared-memory staging in the bucket sorts
+    int flags;            // development switches (QE_FLOW_FLAGS): 1 = no teams of two warps in the bucket sorts (whole-block path for every bucket)
 };
 
 // counter += 1 in shared memory, address space stated (through a pointer the compiler cannot trace to shared memory a plain

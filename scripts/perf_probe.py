@@ -70,12 +70,8 @@ if lib.qe_fused_form(h) == 5 and m >= 4:
     print("  one-pass form: A = select + step + targets (+ bucket counts), B1 = column scan + commit, B2 = sort of the next states; scatter us:",
           " ".join(f"{(buf[32 + k] - ts[2 + 3 * k]) / 1e3:.1f}" for k in range((m - 1) // 3)), "| bucket sorts us:", " ".join(f"{(ts[3 + 3 * k] - buf[32 + k]) / 1e3:.1f}" for k in range((m - 1) // 3)))
 cnt = (C.c_uint64 * 56)()
-if lib.qe_fused_form(h) == 5 and lib.qe_debug_counters(h, cnt, 0) == 0:
-    print('slowest staged bucket: %.1f us, %d keys | slowest unstaged bucket: %.1f us, %d keys | block-path blocks (launch total) %d' % ((cnt[0] >> 13) * 64 / 1e3, cnt[0] & 8191, (cnt[1] >> 13) * 64 / 1e3, cnt[1] & 8191, cnt[2]))
-    lib.qe_debug_counters(h, cnt, 2)
-    print('slowest bucket id', cnt[3] & 1023, 'duration histogram (8 us bins, launch total):', [cnt[8 + j] for j in range(16)])
+if lib.qe_fused_form(h) == 5 and lib.qe_debug_counters(h, cnt, 2) == 0 and cnt[16]:  # only a -DQE_FLOW_STATS build counts
     print('in-order pass (launch totals, warp-passes; lane counts / 32): passes %d busy %d progress %d blocked %d fresh %d produce %d' % tuple(cnt[16 + j] for j in range(6)))
-    print('slow by warp', [cnt[24 + j] for j in range(8)], 'by block eighth', [cnt[32 + j] for j in range(8)], 'slow by size/256', [cnt[40 + j] for j in range(8)], 'fast by size/256', [cnt[48 + j] for j in range(8)])
 if lib.qe_fused_form(h) == 3:
     if lib.qe_debug_counters(h, cnt, 2) == 0 and cnt[0]:
         print("sort laps of block 0, us per sort (hist, barrier, column scan, barrier, bases, scatter, barrier): pass 0", [round(cnt[8 + j] / 1e3 / K, 1) for j in range(7)],
