@@ -543,7 +543,7 @@ __host__ __device__ constexpr size_t flow_smem_bytes(int lpr) {
            kFlowExtraBytes;
 }
 #ifndef QE_FLOW_CLAIM
-#define QE_FLOW_CLAIM 2
+#define QE_FLOW_CLAIM 1
 #endif
 #ifndef QE_FLOW_MIN_BLOCKS
 #define QE_FLOW_MIN_BLOCKS 3
@@ -620,8 +620,9 @@ __global__ void __launch_bounds__(256, QE_FLOW_MIN_BLOCKS) fused_flow_kernel(Tab
         {
             unsigned int* claim = X.ctr;
             float* myrow = s_rows + threadIdx.x * RS;
-            // chunks are claimed kClaim at a time (ONE counter serves the whole grid; same-address atomics are ~2 ns apiece) and
-            // the claim after the current one is always in flight: nobody waits for the counter's round trip
+            // chunks are claimed kClaim at a time (one: two per atomic halve the traffic on the one counter but make the last wave
+            // of the pass -- the tail everybody waits for -- coarser: ~1.5 us slower) and the claim after the current one is
+            // always in flight: nobody waits for the counter's round trip
             constexpr int kClaim = QE_FLOW_CLAIM;
             auto claim_raw = [&]() {  // lane 0's answer; nobody waits for it before it is needed
                 int c = 0;
