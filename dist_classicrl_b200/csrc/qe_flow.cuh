@@ -467,7 +467,7 @@ template <int WARPS>
 __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char* arena, int arena_bytes, const int* s_base, int* s_wsum,
                                              const FlowScratch& X) {
     const int L = X.local_passes;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     const int b = blockIdx.x, nb = gridDim.x;
     const bool teams = (kRadix - 1) / nb < 3 && L == 1 && !(X.flags & 1);
     const int slot_bytes = (arena_bytes / 3) & ~15;
