@@ -51,7 +51,8 @@ struct FlowScratch {
     int local_passes;     // LSD passes (kRadixBits each) over the low msd_shift bits inside a bucket
     int sorted_valid;     // pos / seg / kv[0] / rec describe the states this launch starts from (to be checked)
     int old_n;            // agents of the order kv[0] and seg[] still describe (0: none, seg[] is all-empty)
-    int flags;            // development switches (QE_FLOW_FLAGS): 1 = no teams of two warps in the bucket sorts (whole-block path for every bucket)
+    int flags;            // development / test switches (QE_FLOW_FLAGS): 1 = no teams of two warps in the bucket sorts (whole-block path for
+                          // every bucket), 4 = the shared-memory block path only takes buckets of <= 64 keys (the rest: global-memory passes)
 };
 
 // counter += 1 in shared memory, address space stated (through a pointer the compiler cannot trace to shared memory a plain
@@ -504,7 +505,7 @@ __device__ __forceinline__ void flow_buckets(int (*whist)[kRadix], unsigned char
         }
     }
     if (!__syncthreads_or(rest)) return;
-    const int block_cap = min(flow_block_cap(arena_bytes), 65535);
+    const int block_cap = (X.flags & 4) ? 64 : min(flow_block_cap(arena_bytes), 65535);  // (QE_FLOW_FLAGS & 4: tests push ordinary buckets through the global-memory passes)
     for (int d = b; d < kRadix; d += nb) {
         const int lo = s_base[d], hi = s_base[d + 1];
         if (hi <= lo || (teams ? hi - lo <= stage_cap : hi - lo <= 32)) continue;  // (uniform; the teams / single warps have done theirs)

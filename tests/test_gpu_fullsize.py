@@ -174,6 +174,29 @@ def test_all_forms_of_the_fused_update_match_the_oracle(capi, monkeypatch, form,
         r.close()
 
 
+@pytest.mark.parametrize("flags", ["1", "5"])
+@pytest.mark.parametrize("S,A,N,steps", [(2000, 16, 50_000, 12), (300_000, 8, 200_000, 8), (3, 20, 1000, 6), (3_000_000, 4, 150_000, 6), (1_000_000, 16, 1 << 18, 6)])
+def test_one_pass_form_every_bucket_sort_path_matches_the_oracle(capi, monkeypatch, flags, S, A, N, steps):
+    """The next step's order is built by whichever bucket sort fits: teams of two warps, one warp for tiny buckets, the whole
+    block in shared memory, counting passes through global memory for what does not fit there.  QE_FLOW_FLAGS = 1 takes the
+    teams out, 5 also limits the shared-memory path to 64 keys, so that ordinary buckets exercise the other paths (one low
+    digit, two low digits with the copy back, no low bits at all); the results must not change."""
+    monkeypatch.setenv("QE_FORM", "5")
+    monkeypatch.setenv("QE_FLOW_FLAGS", flags)
+    seed = 11
+    q_o, st_o, rew_o, _ = _oracle(S, A, N, steps, seed, 1)
+    r = Run(capi, S, A, N, seed, 1)
+    try:
+        r.steps(steps // 2)
+        r.steps(steps - steps // 2)
+        assert capi.lib().qe_fused_form(r.h) == 5
+        assert np.array_equal(r.states.cpu().numpy(), st_o)
+        assert np.array_equal(r.ep.cpu().numpy(), rew_o)
+        assert np.array_equal(r.table(), q_o)
+    finally:
+        r.close()
+
+
 @pytest.mark.parametrize("S,A,N,steps", [(19, 4, 1, 60), (500, 9, 128, 200), (40, 32, 256, 50), (5000, 16, 255, 64), (3, 8, 200, 30)])
 def test_small_batches_one_cta_loop_matches_the_oracle(capi, monkeypatch, S, A, N, steps):
     """Batches of at most 256 agents run in one CTA (csrc/qe_small.cuh): same results as the oracle, whatever the crowding."""
