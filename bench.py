@@ -799,6 +799,30 @@ def run_ours(args) -> dict | None:
            f"run_steps({call_steps}, env, state_dict): the step's pre-drawn uniforms (PredrawnUniforms, pinned host memory) and the state dict's running returns go host->device, the returns and the episode statistics come back, every step"}
     del algo, env, runner, rt
 
+    # The same call with the engine's own counter stream instead of pre-drawn uniforms: the only per-step host traffic left is
+    # the state dictionary's running returns (4 bytes per agent each way) -- what a caller that does not inject a random
+    # stream gets.  Reported beside `e2e`, never instead of it (N = 1 only; a failure here must not cost the line).
+    e2e_engine_rng = None
+    if world == 1:
+        try:
+            algo, env = make()
+            rt = SingleThreadQLearning(algo, ConstantSchedule(LR), ConstantSchedule(EPS))
+            rt.history_mode = "summary"
+            sd = {"states": None, "infos": {}, "rewards": np.zeros(n, dtype=np.float32)}
+            for _ in range(max(1, We // call_steps)):
+                _, _, _, sd = rt.run_steps(call_steps, env, sd)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(Ke // call_steps):
+                _, _, _, sd = rt.run_steps(call_steps, env, sd)
+            torch.cuda.synchronize()
+            es = time.perf_counter() - t0
+            e2e_engine_rng = {"value": n * Ke / es, "unit": "agent-steps/s", "h2d_bytes_per_step": n * 4 + 12, "d2h_bytes_per_step": n * 4 + 16, "steps": Ke,
+                              "api": f"SingleThreadQLearning.run_steps({call_steps}, env, state_dict) with the engine's counter stream: only the state dict's running returns travel, both ways, every step"}
+            del algo, env, rt
+        except Exception as exc:  # noqa: BLE001
+            e2e_engine_rng = {"value": None, "error": repr(exc)[:200]}
+
     # ---------------- sharded 100M-state table (config 4): peer memory over NVLink, one persistent kernel per GPU
     sharded = None
     parity = None
@@ -911,7 +935,7 @@ def run_ours(args) -> dict | None:
     out = {
         "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": cfg, "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+        "data": "synthetic", "config": cfg, "roofline": roofline, "e2e": e2e, "e2e_engine_rng": e2e_engine_rng, "gpu_launches": gpu_launches, "clocks": clocks,
         "episodes": episodes,
     }
     if value_long is not None:
