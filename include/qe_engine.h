@@ -240,7 +240,8 @@ int32_t qe_fused_form(qe_engine_t* e);
 int qe_set_fused_form(qe_engine_t* e, int32_t form);
 /* phase clock of the last fused launch (synchronous): out_host[0] = %globaltimer (ns) at kernel start, then for each
  * of the first 10 vector steps the time after phase A (select + env step + writer registration), after phase B1 (TD
- * update, first pass) and after phase B2 (TD update, deferred agents).  Returns the number of values written. */
+ * update, first pass) and after phase B2 (TD update, deferred agents).  One-pass form (5): after the in-order pass, after
+ * the commit, after the bucket sorts; out_host[32 + k] = after the scatter of step k.  Returns the number of values written. */
 int32_t qe_fused_phase_ns(qe_engine_t* e, uint64_t* out_host, int32_t cap);
 /* GB/s of dependency-free random whole-row gathers over this table (the ceiling of the engine's dominant access pattern;
  * bench.py: roofline.gather_peak) */
